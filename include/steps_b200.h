@@ -1,0 +1,161 @@
+/* steps_b200.h -- C ABI of libstepsb200.so, the B200-native direct-summation gravity engine
+ * that replaces the O(N^2) force path (and the KDK step wrapped around it) of eltevo/StePS.
+ *
+ * Everything here is `extern "C"`, plain pointers and sizes.  Citations are to the reference tree
+ * (StePS/src/...) and name the interface each entry point replaces.
+ *
+ * Conventions shared by all calls
+ *   - REAL is `double` for the *_f64 entry points and `float` for *_f32 (reference:
+ *     global_variables.h:26-32, -DUSE_SINGLE_PRECISION).
+ *   - positions/velocities/forces are AoS, x[3*i+k] (reference: global `x`, `v`, `F`).
+ *   - every function returns 0 on success, non-zero on failure; steps_b200_last_error() then
+ *     returns a message.  The reference's convention (print to stderr, set ForceError=true, return;
+ *     forces_cuda.cu:970-974, main.cc:1851-1856) is restored by the C++ shim (shim_steps.cc).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with an error.
+ */
+#ifndef STEPS_B200_H
+#define STEPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STEPS_B200_ABI_VERSION 1
+
+/* topology = which reference build is being replaced (Template-LinuxGCC-Makefile:23-47) */
+enum {
+    STEPS_TOPO_R3 = 0,          /* no flag           : forces()            forces.cc:510 / forces_cuda.cu:522 */
+    STEPS_TOPO_T3 = 1,          /* -DPERIODIC        : forces_periodic()   forces.cc:776 / forces_cuda.cu:567 */
+    STEPS_TOPO_S1R2_LOOKUP = 2, /* -DPERIODIC_Z      : forces_periodic_z() forces.cc:1305 / forces_cuda.cu:764 */
+    STEPS_TOPO_S1R2_NOLOOKUP = 3/* -DPERIODIC_Z -DPERIODIC_Z_NOLOOKUP      forces.cc:1250 / forces_cuda.cu:652 */
+};
+
+/* The globals the reference force path reads at link time (`nm -u forces.o`),
+ * packed into one POD.  Table pointers are HOST pointers; the engine uploads them once. */
+typedef struct steps_b200_params {
+    int32_t abi_version;        /* = STEPS_B200_ABI_VERSION */
+    int32_t topology;           /* STEPS_TOPO_* */
+    int32_t n;                  /* N */
+    int32_t cosmology;          /* COSMOLOGY */
+    int32_t comoving;           /* COMOVING_INTEGRATION */
+    int32_t is_periodic;        /* IS_PERIODIC */
+    int32_t s1r2_interp_order;  /* EWALD_INTERPOLATION_ORDER for the S^1xR^2 lookup build: 0 NGP, 2 CIC, 4 TSC
+                                   (forces_cuda.cu:435-447); T^3 is always tricubic (main.cc:498-502) */
+    int32_t table_dim0;         /* T^3: N_EWALD_FORCE_GRID;  S^1xR^2 lookup: Nrho_EWALD_FORCE_GRID */
+    int32_t table_dim1;         /* S^1xR^2 lookup: Nz_EWALD_FORCE_GRID */
+    int32_t radial_table_size;  /* RADIAL_FORCE_TABLE_SIZE */
+    double L;                   /* L (box size / z period) */
+    double Rsim;                /* Rsim */
+    double mass_in_unit_sphere; /* mass_in_unit_sphere (main.cc:1269,1288,1313) */
+    double H0;                  /* H0 (internal units) */
+    double Omega_lambda;        /* Omega_lambda; DE = (REAL)H0*H0*Omega_lambda (forces.cc:513) */
+    const void *ewald_table;    /* T3_EWALD_FORCE_TABLE [Ng^3][3] or S1R2_EWALD_FORCE_TABLE [Nrho][Nz][2], REAL */
+    const void *radial_table;   /* RADIAL_FORCE_TABLE [radial_table_size], REAL */
+} steps_b200_params;
+
+const char *steps_b200_last_error(void);
+int steps_b200_abi_version(void);
+/* number of visible CUDA devices (0 when there is no GPU; never an error) */
+int steps_b200_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Stateless parity path.  Replaces
+ *        void forces(REAL*x, REAL*F, int ID_min, int ID_max)            forces_cuda.cu:74-78
+ *        void forces_periodic(REAL*x, REAL*F, int ID_min, int ID_max)   forces_cuda.cu:169-173
+ *        void forces_periodic_z(REAL*x, REAL*F, int ID_min, int ID_max) forces_cuda.cu:457-461
+ *     x: host AoS [3N]; M, soft: host [N] (globals M, SOFT_LENGTH); F: host [3*(id_max-id_min+1)],
+ *     fully overwritten, index relative to id_min.  Device buffers are cached between calls
+ *     (the reference re-mallocs and re-uploads per call, forces_cuda.cu:976-1050).
+ * ------------------------------------------------------------------------------------------ */
+int steps_b200_forces_f64(const steps_b200_params *p, const double *x, const double *M, const double *soft,
+                          double *F, int id_min, int id_max);
+int steps_b200_forces_f32(const steps_b200_params *p, const float *x, const float *M, const float *soft,
+                          float *F, int id_min, int id_max);
+
+/* void calculate_softening_length(REAL*SOFT_LENGTH, REAL*M, int N)  utils.cc:59-82.
+ * Host O(N) helper kept in the library so a caller does not need the reference's utils.o.
+ * Outputs M_min and rho_part as the reference's globals of the same name. */
+int steps_b200_softening_f64(const double *M, int n, double particle_radii, double *soft_out, double *M_min_out,
+                             double *rho_part_out);
+int steps_b200_softening_f32(const float *M, int n, float particle_radii, float *soft_out, float *M_min_out,
+                             float *rho_part_out);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Device-resident engine (north_star item 3): x, v, F, M, s stay in HBM across KDK steps.
+ *     One engine per process per GPU.  Replaces step() (step.cc:100-312), calculate_init_h()
+ *     (step.cc:35-98) and the per-step host<->device traffic of forces_cuda.cu:976-1105.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct steps_b200_engine steps_b200_engine;
+
+/* real_bytes: 8 or 4.  device: CUDA ordinal.  [i_lo, i_hi): the i-particles this engine owns
+ * (pass 0, n for a single GPU); see steps_b200_partition(). */
+int steps_b200_engine_create(steps_b200_engine **out, const steps_b200_params *p, int real_bytes, int device);
+void steps_b200_engine_destroy(steps_b200_engine *e);
+
+/* contiguous i-partition, remainder spread one-each over the first ranks (replaces main.cc:1581-1607
+ * and forces_cuda.cu:942-951, which give the whole remainder to rank/GPU 0). */
+void steps_b200_partition(int n, int nranks, int rank, int *i_lo, int *i_hi);
+
+/* NCCL bootstrap for one-process-per-GPU runs: rank 0 calls unique_id() and ships the 128 bytes to
+ * the others by any means (MPI_Bcast in StePS, torch.distributed in bench.py); then every rank
+ * calls comm_init().  Without comm_init the engine is single-GPU and owns [0, n). */
+int steps_b200_nccl_unique_id(void *id128);
+int steps_b200_engine_comm_init(steps_b200_engine *e, const void *id128, int rank, int nranks);
+
+/* upload the full state (host AoS x[3N], v[3N]; M[N], soft[N]); REAL = engine precision */
+int steps_b200_engine_upload(steps_b200_engine *e, const void *x, const void *v, const void *M, const void *soft);
+/* only positions (stateless-style use of a resident engine) */
+int steps_b200_engine_upload_x(steps_b200_engine *e, const void *x);
+
+/* forces for i in [id_min, id_max] from the resident positions into the resident F (asynchronous) */
+int steps_b200_engine_forces(steps_b200_engine *e, int id_min, int id_max);
+/* copy the resident F slice [id_min, id_max] to host (synchronises) */
+int steps_b200_engine_download_forces(steps_b200_engine *e, void *F, int id_min, int id_max);
+/* full state to host: any of x, v, F may be NULL.  x, v: [3N]; F: [3N] (rows outside the owned
+ * range are only meaningful after a gather -- multi-GPU callers read their own range). */
+int steps_b200_engine_download(steps_b200_engine *e, void *x, void *v, void *F);
+
+/* calculate_init_h() step.cc:35-98: wraps positions into the box, returns
+ * errmax = max_i |G F a^-3 - 2 H v| / s_i  over ALL particles (max-all-reduced over ranks). */
+int steps_b200_engine_init_errmax(steps_b200_engine *e, double a, double hubble, double *errmax_out);
+
+/* one KDK step, step.cc:100-312:
+ *   kick(h/2; a_old, H_old) -> drift(h) -> periodic wrap -> [position all-gather over NCCL]
+ *   -> forces -> kick(h/2; a_new, H_new) + errmax reduction (device, then max over ranks).
+ * The caller advances the scale factor itself (friedmann_solver_step, step.cc:237-240) -- use
+ * steps_b200_friedmann_step()/steps_b200_hubble() or the reference's own. */
+int steps_b200_engine_kdk_step(steps_b200_engine *e, double h, double a_old, double hubble_old, double a_new,
+                               double hubble_new, double *errmax_out);
+
+/* device timers (CUDA events on the engine's stream): milliseconds of the last force evaluation
+ * (pack + pair kernels + reduce) and of the last complete kdk_step. */
+int steps_b200_engine_timings(steps_b200_engine *e, double *force_ms, double *step_ms);
+/* number of kernel launches issued by the engine so far (bench.py's gpu_launches) */
+long long steps_b200_engine_launch_count(steps_b200_engine *e);
+int steps_b200_engine_sync(steps_b200_engine *e);
+/* launch-shape report for DESIGN/bench: out[0]=i per CTA, out[1]=j chunks, out[2]=CTAs, out[3]=j tile */
+int steps_b200_engine_launch_shape(steps_b200_engine *e, int id_min, int id_max, int *out4);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Host scalars of the integrator, restated so a C/C++ driver needs nothing else:
+ *     friedmann_solver_step / CALCULATE_Hubble_param (friedmann_solver.cc:100-164, LCDM),
+ *     the timestep rule of main.cc:1834-1846.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct steps_b200_cosmo {
+    double H0, Omega_m, Omega_r, Omega_lambda, Omega_k;
+} steps_b200_cosmo;
+double steps_b200_friedmann_step(const steps_b200_cosmo *c, double a0, double h);
+double steps_b200_hubble(const steps_b200_cosmo *c, double a);
+double steps_b200_next_timestep(double acc_param, double errmax, double h_min, double h_max);
+
+/* FP64 / FP32 FMA-pipe microbenchmark on `device`: returns measured TFLOP/s (2 flop per FMA) --
+ * the roofline denominator for this path. */
+int steps_b200_fma_peak(int device, int real_bytes, double *tflops_out, double *sm_clock_mhz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEPS_B200_H */

@@ -1,0 +1,22 @@
+"""steps_b200 -- B200-native direct-summation gravity engine behind StePS's force-call boundary.
+
+The package holds only what the hot path needs: ``csrc/`` (CUDA kernels + the C ABI of
+``include/steps_b200.h``), the ctypes binding (``_lib``), the host-side mirror of the reference's
+force/step interface (``api``) and the synthetic IC shapes of BASELINE.json (``ic``).
+"""
+from ._lib import StepsError, TOPO_R3, TOPO_S1R2_LOOKUP, TOPO_S1R2_NOLOOKUP, TOPO_T3, LIB_PATH  # noqa: F401
+from .api import (  # noqa: F401
+    CALCULATE_Hubble_param,
+    Engine,
+    Globals,
+    UNIT_T,
+    UNIT_V,
+    calculate_softening_length,
+    fma_peak,
+    force_entry,
+    forces,
+    forces_periodic,
+    forces_periodic_z,
+    friedmann_solver_step,
+    partition,
+)

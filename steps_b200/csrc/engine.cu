@@ -1,0 +1,758 @@
+// engine.cu -- host side of libstepsb200.so: the extern "C" layer of include/steps_b200.h,
+// device-resident state, launch planning, NCCL position exchange.  C++ host + CUDA device, as
+// the reference (StePS/src is C++; forces_cuda.cu:878-1704 are its host wrappers).
+//
+// There is NO CPU fallback in this file: every compute entry point needs a CUDA device and
+// fails with an error message otherwise.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+#include <cuda_runtime.h>
+#include <nccl.h>  // types and enums only; the library itself is dlopen'ed at comm_init time
+
+#include "../../include/steps_b200.h"
+#include "aux_kernels.cuh"
+
+using namespace steps;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const std::string &m) {
+    g_err = m;
+    return 1;
+}
+#define CU_TRY(expr)                                                                                          \
+    do {                                                                                                      \
+        cudaError_t e_ = (expr);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr " (" __FILE__ ":" + \
+                        std::to_string(__LINE__) + ")");                                                      \
+    } while (0)
+
+extern "C" const char *steps_b200_last_error(void) { return g_err.c_str(); }
+extern "C" int steps_b200_abi_version(void) { return STEPS_B200_ABI_VERSION; }
+extern "C" int steps_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ NCCL (dlopen)
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail(std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+#define LOADSYM(field, name)                                                      \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name);                           \
+    if (!g_nccl.field) return fail(std::string("libnccl lacks symbol ") + name);
+    LOADSYM(GetUniqueId, "ncclGetUniqueId")
+    LOADSYM(CommInitRank, "ncclCommInitRank")
+    LOADSYM(CommDestroy, "ncclCommDestroy")
+    LOADSYM(Broadcast, "ncclBroadcast")
+    LOADSYM(AllReduce, "ncclAllReduce")
+    LOADSYM(GroupStart, "ncclGroupStart")
+    LOADSYM(GroupEnd, "ncclGroupEnd")
+    LOADSYM(GetErrorString, "ncclGetErrorString")
+#undef LOADSYM
+    return 0;
+}
+#define NCCL_TRY(expr)                                                                             \
+    do {                                                                                           \
+        ncclResult_t r_ = (expr);                                                                  \
+        if (r_ != ncclSuccess) return fail(std::string("NCCL error: ") + g_nccl.GetErrorString(r_) + " at " #expr); \
+    } while (0)
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ launch planning
+namespace {
+// tuned R^3 FP64 kernel shape
+constexpr int F64_R = 4, F64_THREADS = 256, F64_TJ = 128, F64_STAGES = 3, F64_MINB = 2;
+// exact-branch kernels
+constexpr int GEN_R = 2, GEN_THREADS = 128, GEN_TJ = 128, GEN_STAGES = 3;
+constexpr int TJ = 128;  // j-tile (records) shared by all kernels so that one packed array serves all
+static_assert(F64_TJ == TJ && GEN_TJ == TJ, "one tile size");
+constexpr int MIN_TILES_PER_CHUNK = 8;
+
+struct Plan {
+    int ib_size, n_ib, n_chunks, tiles_per_chunk, n_tiles, ctas, slots;
+};
+
+// Work units are (i-block, j-chunk) pairs of equal cost; the grid is dispatched in waves of `slots`
+// resident CTAs, so time ~ ceil(units/slots) * tiles_per_chunk.  Pick the chunk count that minimises it.
+Plan make_plan(int n_i, int n, int ib_size, int slots, size_t real_bytes) {
+    Plan p{};
+    p.ib_size = ib_size;
+    p.n_ib = (n_i + ib_size - 1) / ib_size;
+    p.n_tiles = (n + TJ - 1) / TJ;
+    p.slots = slots;
+    const int cmax = std::max(1, std::min(p.n_tiles / MIN_TILES_PER_CHUNK, 1024));
+    const size_t mem_cap = (size_t)3 << 30;  // partial-sum buffer budget
+    long long best = -1;
+    for (int c = 1; c <= cmax; ++c) {
+        const int tpc = (p.n_tiles + c - 1) / c;
+        const int ce = (p.n_tiles + tpc - 1) / tpc;
+        if ((size_t)ce * 3 * (size_t)n_i * real_bytes > mem_cap && c > 1) break;
+        const long long units = (long long)p.n_ib * ce;
+        const long long waves = (units + slots - 1) / slots;
+        const long long cost = waves * tpc;
+        if (best < 0 || cost < best) {
+            best = cost;
+            p.n_chunks = ce;
+            p.tiles_per_chunk = tpc;
+        }
+    }
+    p.ctas = p.n_ib * p.n_chunks;
+    return p;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ engine
+struct steps_b200_engine {
+    steps_b200_params p{};
+    int real_bytes = 8;
+    int device = 0;
+    int n = 0, n_pad = 0, n_tiles = 0;
+    int num_sms = 148;
+    int i_lo = 0, i_hi = 0, rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t stream = nullptr;
+    void *d_x = nullptr, *d_v = nullptr, *d_F = nullptr, *d_m = nullptr, *d_s = nullptr;
+    void *d_jrec = nullptr, *d_smax = nullptr, *d_fpart = nullptr, *d_table = nullptr, *d_radial = nullptr;
+    double *d_errmax = nullptr, *h_errmax = nullptr;
+    size_t fpart_bytes = 0;
+    const void *h_table_src = nullptr, *h_radial_src = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    long long launches = 0;
+    bool have_state = false;
+    TopoParams tp{};
+};
+
+namespace {
+size_t table_elems(const steps_b200_params &p) {
+    if (p.topology == STEPS_TOPO_T3) return (size_t)p.table_dim0 * p.table_dim0 * p.table_dim0 * 3;
+    if (p.topology == STEPS_TOPO_S1R2_LOOKUP) return (size_t)p.table_dim0 * p.table_dim1 * 2;
+    return 0;
+}
+
+int check_params(const steps_b200_params *p) {
+    if (!p) return fail("params is NULL");
+    if (p->abi_version != STEPS_B200_ABI_VERSION) return fail("steps_b200_params.abi_version mismatch");
+    if (p->topology < 0 || p->topology > 3) return fail("unknown topology");
+    if (p->n <= 0) return fail("n must be positive");
+    if ((long long)p->n * 3 > 2147483647LL) return fail("n too large: 3*n must fit an int (reference limit, main.cc:1208)");
+    if (p->topology != STEPS_TOPO_R3 && p->is_periodic < 1) return fail("periodic topology needs IS_PERIODIC >= 1 (main.cc:405,537)");
+    if (p->topology == STEPS_TOPO_R3 && p->is_periodic != 0) return fail("R^3 build needs IS_PERIODIC == 0 (main.cc:728-733)");
+    if (p->topology == STEPS_TOPO_T3 && p->is_periodic >= 2 && (!p->ewald_table || p->table_dim0 < 1))
+        return fail("T^3 with IS_PERIODIC>=2 needs T3_EWALD_FORCE_TABLE");
+    if (p->topology == STEPS_TOPO_S1R2_LOOKUP && p->is_periodic >= 2 && (!p->ewald_table || p->table_dim0 < 1 || p->table_dim1 < 1))
+        return fail("S^1xR^2 lookup build with IS_PERIODIC>=2 needs S1R2_EWALD_FORCE_TABLE");
+    const bool comoving = p->cosmology == 1 && p->comoving == 1;
+    if ((p->topology == STEPS_TOPO_S1R2_NOLOOKUP || (p->topology == STEPS_TOPO_S1R2_LOOKUP && p->is_periodic == 1)) && comoving &&
+        (!p->radial_table || p->radial_table_size < 2))
+        return fail("S^1xR^2 comoving run needs RADIAL_FORCE_TABLE");
+    return 0;
+}
+
+void fill_topo(steps_b200_engine *e) {
+    const steps_b200_params &p = e->p;
+    TopoParams &t = e->tp;
+    t.topology = p.topology;
+    t.is_periodic = p.is_periodic;
+    t.order = p.s1r2_interp_order;
+    t.dim0 = p.table_dim0;
+    t.dim1 = p.table_dim1;
+    t.radial_size = p.radial_table_size;
+    t.ewald_max = p.is_periodic + 1;
+    t.L = p.L;
+    t.Rsim = p.Rsim;
+    if (e->real_bytes == 4) {
+        t.ewald_cut = (double)(((float)t.ewald_max) - 0.4f);   // REAL arithmetic, main.cc:1271
+        t.rho_max = (double)(float)(2.25 * (float)p.Rsim);     // EWALD_LOOKUP_TABLE_RADIAL_EXTENT_FACTOR*Rsim
+    } else {
+        t.ewald_cut = ((double)t.ewald_max) - 0.4;
+        t.rho_max = 2.25 * p.Rsim;
+    }
+    t.bg_mode = 0;
+    t.bg_coeff = 0.0;
+    if (p.cosmology == 1 && p.comoving == 1) {
+        t.bg_mode = 1;
+        t.bg_coeff = p.mass_in_unit_sphere;
+    } else if (p.cosmology == 1 && p.comoving == 0) {
+        t.bg_mode = 2;
+        // REAL DE = (REAL) H0*H0*Omega_lambda  (forces.cc:513): the cast binds to H0 only
+        t.bg_coeff = (e->real_bytes == 4) ? (double)(float)((double)(float)p.H0 * p.H0 * p.Omega_lambda) : p.H0 * p.H0 * p.Omega_lambda;
+    }
+    if (p.topology == STEPS_TOPO_T3) t.bg_mode = 0;  // no background term in T^3 (forces_cuda.cu:567-645)
+    t.table = e->d_table;
+    t.radial = e->d_radial;
+}
+
+int upload_tables(steps_b200_engine *e) {
+    const steps_b200_params &p = e->p;
+    const size_t ne = table_elems(p);
+    const bool need_table = ne > 0 && p.is_periodic >= 2 && p.ewald_table;
+    if (need_table && p.ewald_table != e->h_table_src) {
+        if (e->d_table) CU_TRY(cudaFree(e->d_table));
+        CU_TRY(cudaMalloc(&e->d_table, ne * e->real_bytes));
+        CU_TRY(cudaMemcpy(e->d_table, p.ewald_table, ne * e->real_bytes, cudaMemcpyHostToDevice));
+        e->h_table_src = p.ewald_table;
+    }
+    if (p.radial_table && p.radial_table_size > 0 && p.radial_table != e->h_radial_src) {
+        if (e->d_radial) CU_TRY(cudaFree(e->d_radial));
+        CU_TRY(cudaMalloc(&e->d_radial, (size_t)p.radial_table_size * e->real_bytes));
+        CU_TRY(cudaMemcpy(e->d_radial, p.radial_table, (size_t)p.radial_table_size * e->real_bytes, cudaMemcpyHostToDevice));
+        e->h_radial_src = p.radial_table;
+    }
+    fill_topo(e);
+    return 0;
+}
+
+template <typename T>
+int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
+    using JRec = typename JRecOf<T>::type;
+    const bool tuned_f64 = (sizeof(T) == 8 && e->p.topology == STEPS_TOPO_R3);
+    const int ib = tuned_f64 ? F64_R * F64_THREADS : GEN_R * GEN_THREADS;
+    const int slots = e->num_sms * (tuned_f64 ? F64_MINB : 4);
+    Plan pl = make_plan(n_i, e->n, ib, slots, sizeof(T));
+    plan_out = pl;
+    const size_t need = (size_t)pl.n_chunks * 3 * (size_t)n_i * sizeof(T);
+    if (need > e->fpart_bytes) {
+        if (e->d_fpart) CU_TRY(cudaFree(e->d_fpart));
+        CU_TRY(cudaMalloc(&e->d_fpart, need));
+        e->fpart_bytes = need;
+    }
+    R3LaunchArgs a{};
+    a.jrec = e->d_jrec;
+    a.fpart = e->d_fpart;
+    a.id_min = id_min;
+    a.n_i = n_i;
+    a.n_ib = pl.n_ib;
+    a.tiles_per_chunk = pl.tiles_per_chunk;
+    a.n_tiles = pl.n_tiles;
+    a.n_j = e->n;
+    a.fstride = n_i;
+    if (tuned_f64) {
+        auto kern = force_r3_f64_kernel<F64_R, F64_THREADS, F64_TJ, F64_STAGES, F64_MINB>;
+        const size_t smem = (size_t)F64_STAGES * F64_TJ * sizeof(JRec64) + 2 * F64_STAGES * sizeof(uint64_t);
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<pl.ctas, F64_THREADS, smem, e->stream>>>(a);
+    } else {
+        const size_t smem = (size_t)GEN_STAGES * GEN_TJ * sizeof(JRec) + 2 * GEN_STAGES * sizeof(uint64_t);
+#define LAUNCH_GEN(TOPO)                                                                                  \
+    {                                                                                                     \
+        auto kern = force_generic_kernel<T, TOPO, GEN_R, GEN_THREADS, GEN_TJ, GEN_STAGES>;                \
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        kern<<<pl.ctas, GEN_THREADS, smem, e->stream>>>(a, e->tp);                                        \
+    }
+        switch (e->p.topology) {
+            case STEPS_TOPO_R3: LAUNCH_GEN(0) break;
+            case STEPS_TOPO_T3: LAUNCH_GEN(1) break;
+            case STEPS_TOPO_S1R2_LOOKUP: LAUNCH_GEN(2) break;
+            default: LAUNCH_GEN(3) break;
+        }
+#undef LAUNCH_GEN
+    }
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    // deterministic chunk reduction + background term
+    reduce_kernel<T><<<(n_i + 255) / 256, 256, 0, e->stream>>>(static_cast<const T *>(e->d_fpart), pl.n_chunks, n_i, n_i, id_min,
+                                                                static_cast<const T *>(e->d_x), static_cast<T *>(e->d_F), e->tp);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int pack(steps_b200_engine *e) {
+    const int blocks = (e->n_pad + 255) / 256;
+    if (e->real_bytes == 8)
+        pack_kernel_f64<<<blocks, 256, 0, e->stream>>>((const double *)e->d_x, (const double *)e->d_m, (const double *)e->d_s,
+                                                       (const double *)e->d_smax, (JRec64 *)e->d_jrec, e->n, e->n_pad, TJ);
+    else
+        pack_kernel_f32<<<blocks, 256, 0, e->stream>>>((const float *)e->d_x, (const float *)e->d_m, (const float *)e->d_s,
+                                                       (const float *)e->d_smax, (JRec32 *)e->d_jrec, e->n, e->n_pad, TJ);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int forces_impl(steps_b200_engine *e, int id_min, int id_max) {
+    if (!e->have_state) return fail("engine has no particle state: call upload first");
+    if (id_min < 0 || id_max >= e->n || id_max < id_min) return fail("bad [id_min, id_max]");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaEventRecord(e->ev[0], e->stream));
+    if (pack(e)) return 1;
+    Plan pl;
+    const int n_i = id_max - id_min + 1;
+    int rc = (e->real_bytes == 8) ? launch_pair<double>(e, id_min, n_i, pl) : launch_pair<float>(e, id_min, n_i, pl);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(e->ev[1], e->stream));
+    return 0;
+}
+
+KdkScalars kdk_scalars(const steps_b200_engine *e, double h, double a, double hubble) {
+    KdkScalars k{};
+    if (e->real_bytes == 4) {
+        k.a3inv = (double)(float)pow(a, -3.0);
+        k.twoH = 2.0 * (double)(float)hubble;
+        k.hhalf = (double)(float)(h / 2.0);
+        k.h = (double)(float)h;
+    } else {
+        k.a3inv = pow(a, -3.0);
+        k.twoH = 2.0 * hubble;
+        k.hhalf = h / 2.0;
+        k.h = h;
+    }
+    k.L = e->p.L;
+    k.G = 1.0;
+    k.topology = e->p.topology;
+    return k;
+}
+
+int gather_positions(steps_b200_engine *e) {
+    if (e->nranks <= 1) return 0;
+    const ncclDataType_t dt = e->real_bytes == 8 ? ncclFloat64 : ncclFloat32;
+    NCCL_TRY(g_nccl.GroupStart());
+    for (int r = 0; r < e->nranks; ++r) {
+        int lo, hi;
+        steps_b200_partition(e->n, e->nranks, r, &lo, &hi);
+        char *ptr = static_cast<char *>(e->d_x) + (size_t)3 * lo * e->real_bytes;
+        NCCL_TRY(g_nccl.Broadcast(ptr, ptr, (size_t)3 * (hi - lo), dt, r, e->comm, e->stream));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    return 0;
+}
+
+int reduce_errmax(steps_b200_engine *e, double *out) {
+    if (e->nranks > 1) NCCL_TRY(g_nccl.AllReduce(e->d_errmax, e->d_errmax, 1, ncclFloat64, ncclMax, e->comm, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->h_errmax, e->d_errmax, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaEventRecord(e->ev[3], e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    *out = *e->h_errmax;
+    return 0;
+}
+}  // namespace
+
+extern "C" void steps_b200_partition(int n, int nranks, int rank, int *i_lo, int *i_hi) {
+    const int base = n / nranks, rem = n % nranks;
+    const int lo = rank * base + (rank < rem ? rank : rem);
+    *i_lo = lo;
+    *i_hi = lo + base + (rank < rem ? 1 : 0);
+}
+
+extern "C" int steps_b200_engine_create(steps_b200_engine **out, const steps_b200_params *p, int real_bytes, int device) {
+    if (!out) return fail("out is NULL");
+    *out = nullptr;
+    if (check_params(p)) return 1;
+    if (real_bytes != 8 && real_bytes != 4) return fail("real_bytes must be 8 or 4");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail("no CUDA device available: libstepsb200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail("bad device ordinal");
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(std::string("device ") + prop.name + " is not sm_100 class: this library is built for sm_100a only");
+    auto *e = new steps_b200_engine();
+    e->p = *p;
+    e->real_bytes = real_bytes;
+    e->device = device;
+    e->n = p->n;
+    e->n_tiles = (p->n + TJ - 1) / TJ;
+    e->n_pad = e->n_tiles * TJ;
+    e->num_sms = prop.multiProcessorCount;
+    e->i_lo = 0;
+    e->i_hi = p->n;
+    const size_t rb = real_bytes, n = p->n;
+    const size_t jrec_bytes = (real_bytes == 8 ? sizeof(JRec64) : sizeof(JRec32)) * (size_t)e->n_pad;
+#define E_TRY(expr)                                  \
+    do {                                             \
+        cudaError_t e_ = (expr);                     \
+        if (e_ != cudaSuccess) {                     \
+            steps_b200_engine_destroy(e);            \
+            return fail(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr); \
+        }                                            \
+    } while (0)
+    E_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    E_TRY(cudaMalloc(&e->d_x, 3 * n * rb));
+    E_TRY(cudaMalloc(&e->d_v, 3 * n * rb));
+    E_TRY(cudaMalloc(&e->d_F, 3 * n * rb));
+    E_TRY(cudaMalloc(&e->d_m, n * rb));
+    E_TRY(cudaMalloc(&e->d_s, n * rb));
+    E_TRY(cudaMalloc(&e->d_smax, (size_t)e->n_tiles * rb));
+    E_TRY(cudaMalloc(&e->d_jrec, jrec_bytes));
+    E_TRY(cudaMalloc(&e->d_errmax, sizeof(double)));
+    E_TRY(cudaMallocHost(&e->h_errmax, sizeof(double)));
+    E_TRY(cudaMemset(e->d_F, 0, 3 * n * rb));
+    E_TRY(cudaMemset(e->d_v, 0, 3 * n * rb));
+    for (auto &ev : e->ev) E_TRY(cudaEventCreate(&ev));
+#undef E_TRY
+    if (upload_tables(e)) {
+        steps_b200_engine_destroy(e);
+        return 1;
+    }
+    *out = e;
+    return 0;
+}
+
+extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax};
+    for (void *b : bufs)
+        if (b) cudaFree(b);
+    if (e->h_errmax) cudaFreeHost(e->h_errmax);
+    for (auto &ev : e->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int steps_b200_nccl_unique_id(void *id128) {
+    if (nccl_load()) return 1;
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+extern "C" int steps_b200_engine_comm_init(steps_b200_engine *e, const void *id128, int rank, int nranks) {
+    if (!e) return fail("engine is NULL");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank/nranks");
+    e->rank = rank;
+    e->nranks = nranks;
+    steps_b200_partition(e->n, nranks, rank, &e->i_lo, &e->i_hi);
+    if (nranks == 1) return 0;
+    if (nccl_load()) return 1;
+    CU_TRY(cudaSetDevice(e->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NCCL_TRY(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
+    return 0;
+}
+
+extern "C" int steps_b200_engine_upload(steps_b200_engine *e, const void *x, const void *v, const void *M, const void *soft) {
+    if (!e) return fail("engine is NULL");
+    if (!x || !M || !soft) return fail("x, M, soft must be non-NULL");
+    CU_TRY(cudaSetDevice(e->device));
+    const size_t rb = e->real_bytes, n = e->n;
+    CU_TRY(cudaMemcpyAsync(e->d_x, x, 3 * n * rb, cudaMemcpyHostToDevice, e->stream));
+    if (v) CU_TRY(cudaMemcpyAsync(e->d_v, v, 3 * n * rb, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->d_m, M, n * rb, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->d_s, soft, n * rb, cudaMemcpyHostToDevice, e->stream));
+    const int blocks = (e->n_tiles + 127) / 128;
+    if (rb == 8)
+        tile_smax_kernel<double><<<blocks, 128, 0, e->stream>>>((const double *)e->d_s, e->n, TJ, e->n_tiles, (double *)e->d_smax);
+    else
+        tile_smax_kernel<float><<<blocks, 128, 0, e->stream>>>((const float *)e->d_s, e->n, TJ, e->n_tiles, (float *)e->d_smax);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    e->have_state = true;
+    return 0;
+}
+
+extern "C" int steps_b200_engine_upload_x(steps_b200_engine *e, const void *x) {
+    if (!e) return fail("engine is NULL");
+    if (!e->have_state) return fail("upload_x before upload");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaMemcpyAsync(e->d_x, x, 3 * (size_t)e->n * e->real_bytes, cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+
+extern "C" int steps_b200_engine_forces(steps_b200_engine *e, int id_min, int id_max) {
+    if (!e) return fail("engine is NULL");
+    return forces_impl(e, id_min, id_max);
+}
+
+extern "C" int steps_b200_engine_download_forces(steps_b200_engine *e, void *F, int id_min, int id_max) {
+    if (!e) return fail("engine is NULL");
+    if (id_min < 0 || id_max >= e->n || id_max < id_min) return fail("bad [id_min, id_max]");
+    CU_TRY(cudaSetDevice(e->device));
+    const size_t rb = e->real_bytes;
+    CU_TRY(cudaMemcpyAsync(F, static_cast<char *>(e->d_F) + 3 * (size_t)id_min * rb, 3 * (size_t)(id_max - id_min + 1) * rb,
+                           cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int steps_b200_engine_download(steps_b200_engine *e, void *x, void *v, void *F) {
+    if (!e) return fail("engine is NULL");
+    CU_TRY(cudaSetDevice(e->device));
+    const size_t bytes = 3 * (size_t)e->n * e->real_bytes;
+    if (x) CU_TRY(cudaMemcpyAsync(x, e->d_x, bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (v) CU_TRY(cudaMemcpyAsync(v, e->d_v, bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (F) CU_TRY(cudaMemcpyAsync(F, e->d_F, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+template <typename T>
+static int errmax_launch(steps_b200_engine *e, const KdkScalars &k, int do_kick, int do_wrap) {
+    const int cnt = e->i_hi - e->i_lo;
+    CU_TRY(cudaMemsetAsync(e->d_errmax, 0, sizeof(double), e->stream));
+    kick_errmax_kernel<T><<<(cnt + 255) / 256, 256, 0, e->stream>>>((T *)e->d_x, (T *)e->d_v, (const T *)e->d_F, (const T *)e->d_s,
+                                                                     e->i_lo, e->i_hi, k, do_kick, do_wrap, e->d_errmax);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int steps_b200_engine_init_errmax(steps_b200_engine *e, double a, double hubble, double *errmax_out) {
+    if (!e) return fail("engine is NULL");
+    if (!e->have_state) return fail("engine has no particle state");
+    CU_TRY(cudaSetDevice(e->device));
+    const KdkScalars k = kdk_scalars(e, 0.0, a, hubble);
+    int rc = e->real_bytes == 8 ? errmax_launch<double>(e, k, 0, 1) : errmax_launch<float>(e, k, 0, 1);
+    if (rc) return rc;
+    return reduce_errmax(e, errmax_out);
+}
+
+extern "C" int steps_b200_engine_kdk_step(steps_b200_engine *e, double h, double a_old, double hubble_old, double a_new,
+                                          double hubble_new, double *errmax_out) {
+    if (!e) return fail("engine is NULL");
+    if (!e->have_state) return fail("engine has no particle state");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaEventRecord(e->ev[2], e->stream));
+    const int cnt = e->i_hi - e->i_lo;
+    const KdkScalars k0 = kdk_scalars(e, h, a_old, hubble_old);
+    if (e->real_bytes == 8)
+        kick_drift_kernel<double><<<(cnt + 255) / 256, 256, 0, e->stream>>>((double *)e->d_x, (double *)e->d_v, (const double *)e->d_F,
+                                                                             e->i_lo, e->i_hi, k0);
+    else
+        kick_drift_kernel<float><<<(cnt + 255) / 256, 256, 0, e->stream>>>((float *)e->d_x, (float *)e->d_v, (const float *)e->d_F, e->i_lo,
+                                                                            e->i_hi, k0);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    if (gather_positions(e)) return 1;
+    if (forces_impl(e, e->i_lo, e->i_hi - 1)) return 1;
+    const KdkScalars k1 = kdk_scalars(e, h, a_new, hubble_new);
+    int rc = e->real_bytes == 8 ? errmax_launch<double>(e, k1, 1, 0) : errmax_launch<float>(e, k1, 1, 0);
+    if (rc) return rc;
+    return reduce_errmax(e, errmax_out);
+}
+
+extern "C" int steps_b200_engine_timings(steps_b200_engine *e, double *force_ms, double *step_ms) {
+    if (!e) return fail("engine is NULL");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    float f = 0.f, s = 0.f;
+    if (force_ms) {
+        if (cudaEventElapsedTime(&f, e->ev[0], e->ev[1]) != cudaSuccess) { cudaGetLastError(); f = -1.f; }
+        *force_ms = f;
+    }
+    if (step_ms) {
+        if (cudaEventElapsedTime(&s, e->ev[2], e->ev[3]) != cudaSuccess) { cudaGetLastError(); s = -1.f; }
+        *step_ms = s;
+    }
+    return 0;
+}
+
+extern "C" long long steps_b200_engine_launch_count(steps_b200_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int steps_b200_engine_sync(steps_b200_engine *e) {
+    if (!e) return fail("engine is NULL");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int steps_b200_engine_launch_shape(steps_b200_engine *e, int id_min, int id_max, int *out4) {
+    if (!e) return fail("engine is NULL");
+    const bool tuned_f64 = (e->real_bytes == 8 && e->p.topology == STEPS_TOPO_R3);
+    const int ib = tuned_f64 ? F64_R * F64_THREADS : GEN_R * GEN_THREADS;
+    const int slots = e->num_sms * (tuned_f64 ? F64_MINB : 4);
+    Plan pl = make_plan(id_max - id_min + 1, e->n, ib, slots, e->real_bytes);
+    out4[0] = pl.ib_size;
+    out4[1] = pl.n_chunks;
+    out4[2] = pl.ctas;
+    out4[3] = TJ;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ stateless path
+namespace {
+steps_b200_engine *g_cached[2] = {nullptr, nullptr};
+
+bool same_shape(const steps_b200_params &a, const steps_b200_params &b) {
+    return a.topology == b.topology && a.n == b.n && a.table_dim0 == b.table_dim0 && a.table_dim1 == b.table_dim1 &&
+           a.radial_table_size == b.radial_table_size;
+}
+
+int forces_stateless(const steps_b200_params *p, int real_bytes, const void *x, const void *M, const void *soft, void *F, int id_min,
+                     int id_max) {
+    if (check_params(p)) return 1;
+    if (!x || !M || !soft || !F) return fail("x, M, soft, F must be non-NULL");
+    if (id_min < 0 || id_max >= p->n || id_max < id_min) return fail("bad [id_min, id_max]");
+    steps_b200_engine *&e = g_cached[real_bytes == 8 ? 0 : 1];
+    if (e && !same_shape(e->p, *p)) {
+        steps_b200_engine_destroy(e);
+        e = nullptr;
+    }
+    if (!e) {
+        int dev = 0;
+        if (const char *s = getenv("STEPS_B200_DEVICE")) dev = atoi(s);
+        if (steps_b200_engine_create(&e, p, real_bytes, dev)) return 1;
+    } else {
+        e->p = *p;
+        if (upload_tables(e)) return 1;
+    }
+    if (steps_b200_engine_upload(e, x, nullptr, M, soft)) return 1;
+    if (forces_impl(e, id_min, id_max)) return 1;
+    return steps_b200_engine_download_forces(e, F, id_min, id_max);
+}
+}  // namespace
+
+extern "C" int steps_b200_forces_f64(const steps_b200_params *p, const double *x, const double *M, const double *soft, double *F,
+                                     int id_min, int id_max) {
+    return forces_stateless(p, 8, x, M, soft, F, id_min, id_max);
+}
+extern "C" int steps_b200_forces_f32(const steps_b200_params *p, const float *x, const float *M, const float *soft, float *F, int id_min,
+                                     int id_max) {
+    return forces_stateless(p, 4, x, M, soft, F, id_min, id_max);
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers
+template <typename T>
+static int softening_impl(const T *M, int n, T particle_radii, T *soft_out, T *M_min_out, T *rho_part_out) {
+    if (!M || !soft_out || n <= 0) return fail("bad arguments");
+    const double pi = 3.14159265358979323846264338327950288419716939937510;
+    T M_min = M[0];
+    for (int i = 0; i < n; ++i)
+        if (M_min > M[i]) M_min = M[i];
+    // utils.cc:71-73: double arithmetic, stored to REAL
+    const T rho_part = (T)(M_min / (4.0 * pi * pow((double)particle_radii, 3.0) / 3.0));
+    const T const_beta = (T)(3.0 / rho_part / (4.0 * pi));
+    for (int i = 0; i < n; ++i) soft_out[i] = (T)cbrt(M[i] * const_beta);
+    if (M_min_out) *M_min_out = M_min;
+    if (rho_part_out) *rho_part_out = rho_part;
+    return 0;
+}
+extern "C" int steps_b200_softening_f64(const double *M, int n, double pr, double *s, double *mm, double *rp) {
+    return softening_impl<double>(M, n, pr, s, mm, rp);
+}
+extern "C" int steps_b200_softening_f32(const float *M, int n, float pr, float *s, float *mm, float *rp) {
+    return softening_impl<float>(M, n, pr, s, mm, rp);
+}
+
+// friedmann_solver_step, LCDM parametrisation (friedmann_solver.cc:100-159)
+extern "C" double steps_b200_friedmann_step(const steps_b200_cosmo *c, double a0, double h) {
+    const double Om = c->Omega_m, Or = c->Omega_r, Ol = c->Omega_lambda, Ok = c->Omega_k, H0 = c->H0;
+    double b = a0;
+    if (fabs(Ok) < 1e-9) {
+        auto E2 = [&](double s) { return Om * pow(s, -3.0) + Or * pow(s, -4.0) + Ol; };
+        const double j = E2(b);
+        const double k1 = b * H0 * sqrt(j);
+        const double b2 = b + h * k1 / 2.0;
+        const double l = E2(b2);
+        const double k2 = b2 * H0 * sqrt(l);
+        const double b3 = b + h * k2 / 2.0;
+        const double m = E2(b3);
+        const double k3 = b3 * H0 * sqrt(m);
+        const double b4 = b + h * k3;
+        const double n = E2(b4);
+        const double k4 = b4 * H0 * sqrt(n);
+        const double K = h * (k1 + k2 * 2.0 + k3 * 2.0 + k4) / 6.0;
+        if (j < 0 || l < 0 || m < 0 || n < 0) b = -1;
+        else b += K;
+    } else {
+        auto E2 = [&](double s) { return Om * pow(s, -3.0) + Or * pow(s, -4.0) + Ol + Ok * pow(s, -2.0); };
+        int collapse = (H0 > 0) ? 0 : 1;
+        const double j = E2(b);
+        const double k1 = b * H0 * sqrt(fabs(j));
+        const double b2 = b + h * k1 / 2.0;
+        const double l = E2(b2);
+        const double k2 = b2 * H0 * sqrt(fabs(l));
+        const double b3 = b + h * k2 / 2.0;
+        const double m = E2(b3);
+        const double k3 = b3 * H0 * sqrt(fabs(m));
+        const double b4 = b + h * k3;
+        const double n = E2(b4);
+        const double k4 = b4 * H0 * sqrt(fabs(n));
+        if (j < 0 && l < 0 && m < 0 && n < 0) collapse = 1;
+        const double K = h * (k1 + k2 * 2.0 + k3 * 2.0 + k4) / 6.0;
+        b = (collapse == 0) ? b + K : b - K;
+    }
+    return b;
+}
+
+// CALCULATE_Hubble_param (friedmann_solver.cc:161-164)
+extern "C" double steps_b200_hubble(const steps_b200_cosmo *c, double a) {
+    return c->H0 * sqrt(c->Omega_m * pow(a, -3) + c->Omega_r * pow(a, -4) + c->Omega_lambda + c->Omega_k * pow(a, -2));
+}
+
+// main.cc:1834-1842 (without the output-time clamp of :1843-1846, which belongs to the snapshot scheduler)
+extern "C" double steps_b200_next_timestep(double acc_param, double errmax, double h_min, double h_max) {
+    double h = pow(2 * acc_param / errmax, 0.5);
+    if (h < h_min) h = h_min;
+    else if (h > h_max) h = h_max;
+    return h;
+}
+
+extern "C" int steps_b200_fma_peak(int device, int real_bytes, double *tflops_out, double *sm_clock_mhz_out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail("no CUDA device available");
+    }
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    const int iters = real_bytes == 8 ? (1 << 15) : (1 << 16);
+    void *d = nullptr;
+    CU_TRY(cudaMalloc(&d, (size_t)blocks * threads * 8));
+    cudaEvent_t a, b;
+    CU_TRY(cudaEventCreate(&a));
+    CU_TRY(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU_TRY(cudaEventRecord(a));
+        if (real_bytes == 8) fma_peak_kernel<double><<<blocks, threads>>>((double *)d, iters, 1.0000001, 1e-9);
+        else fma_peak_kernel<float><<<blocks, threads>>>((float *)d, iters, 1.0000001f, 1e-9f);
+        CU_TRY(cudaEventRecord(b));
+        CU_TRY(cudaEventSynchronize(b));
+        float ms;
+        CU_TRY(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    const double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+    if (tflops_out) *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (sm_clock_mhz_out) {
+        // implied clock if the pipe retires 64 (fp64) / 128 (fp32) FMA lanes per SM per cycle
+        const double lanes = real_bytes == 8 ? 64.0 : 128.0;
+        *sm_clock_mhz_out = flops / 2.0 / (best * 1e-3) / (lanes * prop.multiProcessorCount) / 1e6;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    return 0;
+}

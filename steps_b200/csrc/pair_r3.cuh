@@ -1,0 +1,222 @@
+// pair_r3.cuh -- the R^3 (non-periodic, compactified) pair kernels, FP64 and FP32.
+//
+// Replaces ForceKernel (reference forces_cuda.cu:522-563) / the j-loop of forces() (forces.cc:535-556):
+//     F_i = sum_{j=0}^{N-1} m_j * w(r_ij, s_i + s_j) * (x_j - x_i)
+// with w the cubic-spline softened 1/r^3 of force_softening (forces.cc:52-87, forces_cuda.cu:466-519).
+//
+// Design (B200 / sm_100a):
+//   * work unit = (i-block of THREADS*R particles) x (j-chunk of `tiles_per_chunk` tiles); one CTA per unit.
+//     Splitting j gives units fine enough to fill 148 SMs evenly at any N (tail < 1/units-per-slot) and
+//     partial sums are combined afterwards in fixed chunk order (deterministic, see reduce kernel).
+//   * j-tiles (TJ records of 64 B / 32 B) are staged into shared memory by 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx), STAGES deep; one elected thread is the producer.
+//   * each thread keeps R i-particles in registers; a warp walks the tile with broadcast 128-bit
+//     shared loads, so one LDS serves 32*R pairs.
+//   * far-field pair math runs 15 FP64-pipe instructions (the pipe that bounds this kernel):
+//       3 DADD (d = xj - xi), DMUL+2 DFMA (r2), y0 = MUFU.RSQ64H(r2) [SFU, free],
+//       t = y0*y0, e = fma(-r2,t,1), c = t*y0, p = fma(fma(1.875m,e,1.5m),e,m), w = c*p   (6)
+//       3 DFMA accumulate.            m*r^-3 = m*y0^3*(1-e)^(-3/2), |e|<~2^-21, series error ~2.2*e^3 < 1e-18.
+//     (m, 1.5m, 1.875m) are pre-staged per j so the mass multiply costs nothing.
+//   * the softened branch (r < s_i+s_j) and the self pair (r=0) are detected WITHOUT touching the FP64
+//     pipe: an integer compare of the high word of r2 against a conservative per-(i, tile) threshold
+//     (s_i + max_{j in tile} s_j)^2.  Flagged pairs are masked out of the fast accumulation and
+//     re-evaluated exactly (reference branch structure) in a rare deferred pass per sub-block.
+#pragma once
+#include "ptx_helpers.cuh"
+
+namespace steps {
+
+// One j-particle as staged for the FP64 kernels: 64 B, 16 B-aligned halves for LDS.128.
+struct __align__(16) JRec64 {
+    double x, y;        // LDS.128 #1
+    double z, m;        // LDS.128 #2
+    double m15, m1875;  // LDS.128 #3   1.5*m, 1.875*m
+    double s, smax;     // slow path only: softening length, max softening over this record's tile
+};
+static_assert(sizeof(JRec64) == 64, "JRec64 layout");
+
+// FP32: 32 B.
+struct __align__(16) JRec32 {
+    float x, y, z, m;     // LDS.128 #1
+    float s, smax, p0, p1;  // slow path only
+};
+static_assert(sizeof(JRec32) == 32, "JRec32 layout");
+
+// Exact softened kernel, branch structure and operation order of force_softening_cuda
+// (forces_cuda.cu:466-519).  Returns w (without the mass factor).
+template <typename T>
+__device__ __forceinline__ T softened_w(T r, T beta) {
+    const T half_beta = beta * (T)0.5;
+    const T r2 = r * r;
+    const T r3 = r2 * r;
+    T w;
+    if (r >= beta) {
+        w = (T)1.0 / r3;
+    } else if (r > half_beta) {
+        const T b2 = beta * beta, b3 = b2 * beta, b4 = b2 * b2, b5 = b4 * beta, b6 = b3 * b3;
+        const T C0 = (T)(-32.0) / ((T)3.0 * b6);
+        const T C1 = (T)(38.4) / b5;
+        const T C2 = (T)(-48.0) / b4;
+        const T C3 = (T)(64.0) / ((T)3.0 * b3);
+        const T C4 = (T)(-1.0 / 15.0);
+        w = C0 * r3 + C1 * r2 + C2 * r + C3 + C4 * ((T)1.0 / r3);
+    } else {
+        const T b2 = beta * beta, b3 = b2 * beta, b4 = b2 * b2, b5 = b4 * beta, b6 = b3 * b3;
+        const T C0 = (T)(32.0) / b6;
+        const T C1 = (T)(-38.4) / b5;
+        const T C2 = (T)(32.0 / 3.0) / b3;
+        w = C0 * r3 + C1 * r2 + C2;
+    }
+    return w;
+}
+
+struct R3LaunchArgs {
+    const void *jrec;   // JRec64* / JRec32*, padded to a whole number of tiles
+    void *fpart;        // partial sums, [n_chunks][3][fstride]
+    int id_min;         // first i of the call
+    int n_i;            // number of i-particles in the call
+    int n_ib;           // number of i-blocks
+    int tiles_per_chunk;
+    int n_tiles;        // total j tiles
+    int n_j;            // number of real j-particles (N)
+    int fstride;        // >= n_i
+};
+
+template <int R, int THREADS, int TJ, int STAGES, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_kernel(const R3LaunchArgs a) {
+    constexpr int NWARPS = THREADS / 32;
+    constexpr int JB = 16;  // sub-block between slow-path checks
+    static_assert(TJ % JB == 0, "tile must be a whole number of sub-blocks");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    JRec64 *tiles = reinterpret_cast<JRec64 *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * TJ * sizeof(JRec64));
+    uint64_t *empty = full + STAGES;
+
+    const int tid = threadIdx.x;
+    const int jc = blockIdx.x / a.n_ib;  // chunk-major: concurrently running CTAs stream the same j-chunk from L2
+    const int ib = blockIdx.x - jc * a.n_ib;
+    const int t0 = jc * a.tiles_per_chunk;
+    const int t1 = min(t0 + a.tiles_per_chunk, a.n_tiles);
+    const int nt = t1 - t0;
+    const JRec64 *__restrict__ jrec = static_cast<const JRec64 *>(a.jrec);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NWARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int npre = nt < STAGES ? nt : STAGES;
+        for (int t = 0; t < npre; ++t) {
+            mbar_arrive_expect_tx(&full[t], TJ * sizeof(JRec64));
+            tma_load_1d(tiles + (size_t)t * TJ, jrec + (size_t)(t0 + t) * TJ, TJ * sizeof(JRec64), &full[t]);
+        }
+    }
+
+    double xi[R], yi[R], zi[R], si[R], ax[R], ay[R], az[R];
+    int thr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int il = ib * (THREADS * R) + r * THREADS + tid;
+        il = il < a.n_i ? il : a.n_i - 1;
+        const JRec64 me = jrec[a.id_min + il];
+        xi[r] = me.x; yi[r] = me.y; zi[r] = me.z; si[r] = me.s;
+        ax[r] = ay[r] = az[r] = 0.0;
+    }
+
+    for (int t = 0; t < nt; ++t) {
+        const int s = t % STAGES;
+        const uint32_t ph = (uint32_t)(t / STAGES) & 1u;
+        // producer: refill the stage consumed one iteration ago (all warps have very likely left it)
+        if (tid == 0 && t >= 1 && (t - 1 + STAGES) < nt) {
+            const int sp = (t - 1) % STAGES;
+            const uint32_t php = (uint32_t)((t - 1) / STAGES) & 1u;
+            mbar_wait(&empty[sp], php);
+            mbar_arrive_expect_tx(&full[sp], TJ * sizeof(JRec64));
+            tma_load_1d(tiles + (size_t)sp * TJ, jrec + (size_t)(t0 + t - 1 + STAGES) * TJ, TJ * sizeof(JRec64), &full[sp]);
+        }
+        mbar_wait(&full[s], ph);
+        const JRec64 *__restrict__ T = tiles + (size_t)s * TJ;
+        {
+            const double smax = T[0].smax;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double b = si[r] + smax;
+                // conservative: r2 < b*b  =>  hi(r2) <= hi(b*b); one extra ulp of the high word for rounding of b*b
+                thr[r] = __double2hiint(b * b) + 1;
+            }
+        }
+        for (int j0 = 0; j0 < TJ; j0 += JB) {
+            int ymin = 0x7fffffff;  // becomes 0 iff some pair of this sub-block was flagged
+#pragma unroll 2
+            for (int jj = 0; jj < JB; ++jj) {
+                const double2 xy = *reinterpret_cast<const double2 *>(&T[j0 + jj].x);
+                const double2 zm = *reinterpret_cast<const double2 *>(&T[j0 + jj].z);
+                const double2 mm = *reinterpret_cast<const double2 *>(&T[j0 + jj].m15);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const double dx = xy.x - xi[r];
+                    const double dy = xy.y - yi[r];
+                    const double dz = zm.x - zi[r];
+                    double r2 = dx * dx;
+                    r2 = fma(dy, dy, r2);
+                    r2 = fma(dz, dz, r2);
+                    // seed with the near-mask folded in: y0 = 0 for flagged pairs => w = 0 exactly (and no
+                    // inf/NaN from r2 = 0); costs one ISETP + one SEL on the ALU pipe, nothing on the FP64 pipe.
+                    int yh = __double2hiint(rsqrt_seed(r2));
+                    yh = (__double2hiint(r2) <= thr[r]) ? 0 : yh;
+                    ymin = min(ymin, yh);
+                    const double y0 = __hiloint2double(yh, 0);
+                    const double tt = y0 * y0;
+                    const double e = fma(-r2, tt, 1.0);
+                    const double c = tt * y0;
+                    double p = fma(mm.y, e, mm.x);
+                    p = fma(p, e, zm.y);
+                    const double w = c * p;
+                    ax[r] = fma(w, dx, ax[r]);
+                    ay[r] = fma(w, dy, ay[r]);
+                    az[r] = fma(w, dz, az[r]);
+                }
+            }
+            if (ymin == 0) {
+                // rare: re-evaluate the flagged pairs of this sub-block with the reference's exact branches
+                for (int jj = 0; jj < JB; ++jj) {
+                    const JRec64 q = T[j0 + jj];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double dx = q.x - xi[r];
+                        const double dy = q.y - yi[r];
+                        const double dz = q.z - zi[r];
+                        double r2 = dx * dx;
+                        r2 = fma(dy, dy, r2);
+                        r2 = fma(dz, dz, r2);
+                        if (__double2hiint(r2) <= thr[r]) {
+                            const double w = q.m * softened_w<double>(sqrt(r2), si[r] + q.s);
+                            ax[r] = fma(w, dx, ax[r]);
+                            ay[r] = fma(w, dy, ay[r]);
+                            az[r] = fma(w, dz, az[r]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+    }
+
+    double *__restrict__ fp = static_cast<double *>(a.fpart) + (size_t)jc * 3 * a.fstride;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int il = ib * (THREADS * R) + r * THREADS + tid;
+        if (il < a.n_i) {
+            fp[il] = ax[r];
+            fp[a.fstride + il] = ay[r];
+            fp[2 * (size_t)a.fstride + il] = az[r];
+        }
+    }
+}
+
+}  // namespace steps

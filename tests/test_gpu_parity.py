@@ -1,0 +1,254 @@
+"""GPU (B200): the CUDA path, called through the C ABI with host buffers exactly as the reference's
+forces()/forces_periodic()/forces_periodic_z() are called, against
+  - golden vectors produced by the unmodified reference (tests/golden),
+  - the oracle on seeded inputs at sizes it finishes in seconds,
+  - size-independent properties at BASELINE.json's full size (N = 2M).
+Tolerances (north_star): per-particle relative acceleration error 1e-12 (FP64) / 1e-5 (FP32).
+SURVEY.md H2: the reference's own summation noise reaches ~1e-12 of |F_i| for strongly cancelling
+particles at large N, so large-N checks gate on |dF_i| / sum_j |f_ij| <= 1e-12 and on the 99th
+percentile of |dF_i|/|F_i|, and print the maximum."""
+import math
+
+import numpy as np
+import pytest
+
+import steps_b200 as sb
+from helpers import attach_t3_table, load_golden, needs_t3_table, noise_err, rel_err
+from oracle import pyport, pyref
+from steps_b200 import ic
+
+pytestmark = pytest.mark.gpu
+
+FORCE_CASES = ["r3_f64_comoving", "r3_f64_noncomoving", "r3_f64_nocosmo", "r3_f32_comoving", "r3_f64_zoom", "t3_f64_quasi",
+               "t3_f64_ewald", "t3_f32_ewald", "s1r2nl_f64_images", "s1r2nl_f64_quasi", "s1r2nl_f32_images", "s1r2_f64_lookup",
+               "s1r2_f64_lookup_quasi"]
+TOL64, TOL32 = 1e-12, 1e-5
+
+
+def tol(g):
+    return TOL64 if g.REAL == np.float64 else TOL32
+
+
+def gpu_forces(g, x, lo, hi):
+    F = np.full(3 * (hi - lo + 1), np.nan, dtype=g.REAL)
+    sb.force_entry(g)(g, np.ascontiguousarray(x, dtype=g.REAL), F, lo, hi)
+    assert not g.ForceError
+    return F
+
+
+@pytest.mark.parametrize("name", FORCE_CASES)
+def test_golden_forces(name):
+    g, d = load_golden(name)
+    if needs_t3_table(g) and not attach_t3_table(g, d):
+        pytest.skip("T^3 Ewald table needs oracle/_ref")
+    F = gpu_forces(g, d["x"], 0, g.N - 1)
+    e = rel_err(F, d["F"])
+    print(f"{name}: max |dF|/|F| = {e.max():.3e}")
+    assert e.max() < tol(g)
+    lo, hi = int(d["sub_lo"]), int(d["sub_hi"])
+    Fs = gpu_forces(g, d["x"], lo, hi)  # sub-range call: output indexed relative to ID_min, fully overwritten
+    assert rel_err(Fs, d["Fsub"]).max() < tol(g)
+
+
+def oracle_forces(g, x, lo, hi):
+    """the reference itself when its build travelled with the repo, else the plain-C port"""
+    key = (g.topology, 8 if g.REAL == np.float64 else 4)
+    if key in pyref.VARIANT and pyref.available(pyref.VARIANT[key]) and g.topology == 0:
+        r = pyref.Reference(pyref.VARIANT[key])
+        r.configure(g)
+        g.mass_in_unit_sphere = r.scalars()["mass_in_unit_sphere"]
+        return r.forces(x, lo, hi, 0)
+    return pyport.forces(g, x, lo, hi)
+
+
+def test_r3_f64_zoom_geometry_vs_oracle():
+    c = ic.compactified_r3(20000, 64, 250, 42, d_s=105.0)
+    g = c.g
+    Fo = oracle_forces(g, c.x, 0, g.N - 1)
+    F = gpu_forces(g, c.x, 0, g.N - 1)
+    S = pyport.force_norms(g, c.x, 0, g.N - 1)
+    ne, re_ = noise_err(F, Fo, S), rel_err(F, Fo)
+    print(f"N={g.N}: max |dF|/sum|f| = {ne.max():.3e}; |dF|/|F| p50 {np.median(re_):.2e} p99 {np.percentile(re_, 99):.2e} max {re_.max():.2e}")
+    assert ne.max() < TOL64
+    assert np.percentile(re_, 99) < TOL64
+
+
+def test_r3_f32_vs_oracle():
+    c = ic.compactified_r3(12000, 64, 150, 43, np.float32, d_s=105.0)
+    g = c.g
+    Fo = oracle_forces(g, c.x, 0, g.N - 1)
+    F = gpu_forces(g, c.x, 0, g.N - 1)
+    # FP32 accumulates N terms at 6e-8 each in a different (chunked) order than the reference: compare both with FP64 truth
+    g64 = ic.compactified_r3(12000, 64, 150, 43, np.float64, d_s=105.0).g
+    g64.M, g64.SOFT_LENGTH = g.M.astype(np.float64), g.SOFT_LENGTH.astype(np.float64)
+    g64.mass_in_unit_sphere = g.mass_in_unit_sphere
+    x64 = c.x.astype(np.float64)
+    Ft = pyport.forces(g64, x64, 0, g.N - 1)
+    S = pyport.force_norms(g64, x64, 0, g.N - 1)
+    e_gpu, e_ref = noise_err(F, Ft, S), noise_err(Fo, Ft, S)
+    re_ = rel_err(F, Fo)
+    print(f"fp32: |dF|/sum|f| vs fp64 truth: ours {e_gpu.max():.2e}, reference {e_ref.max():.2e}; ours vs reference |dF|/|F| p99 {np.percentile(re_, 99):.2e} max {re_.max():.2e}")
+    assert e_gpu.max() < TOL32
+    assert e_gpu.max() < 3 * e_ref.max() + 1e-7  # no less accurate than the reference's own FP32 sum
+    assert np.percentile(re_, 99) < TOL32
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 1000, 1025])
+def test_ragged_sizes(n):
+    c = ic.random_sphere(n, 50 + n)
+    F = gpu_forces(c.g, c.x, 0, n - 1)
+    Fo = pyport.forces(c.g, c.x, 0, n - 1)
+    assert np.isfinite(F).all()
+    scale = np.abs(Fo).max() + 1e-300
+    assert np.abs(F - Fo).max() / scale < 1e-13
+
+
+def test_single_particle_ranges_and_last_particle():
+    c = ic.random_sphere(777, 8)
+    g = c.g
+    Fall = gpu_forces(g, c.x, 0, g.N - 1)
+    for i in (0, 1, 388, 776):
+        Fi = gpu_forces(g, c.x, i, i)
+        assert rel_err(Fi, Fall[3 * i: 3 * i + 3]).max() < 1e-13
+
+
+def test_coincident_and_fully_softened():
+    c = ic.random_sphere(600, 13, cosmology=0)
+    g = c.g
+    c.x[3:6] = c.x[0:3]          # r = 0 between distinct particles (collision)
+    c.x[30:33] = c.x[60:63]
+    F = gpu_forces(g, c.x, 0, g.N - 1)
+    Fo = pyport.forces(g, c.x, 0, g.N - 1)
+    assert np.isfinite(F).all()
+    assert rel_err(F, Fo).max() < 1e-12
+    # softening larger than the whole system: every pair takes the r <= beta/2 or beta/2 < r < beta branch
+    g.SOFT_LENGTH = np.full(g.N, 40.0)
+    F = gpu_forces(g, c.x, 0, g.N - 1)
+    Fo = pyport.forces(g, c.x, 0, g.N - 1)
+    assert rel_err(F, Fo).max() < 1e-12
+    # mixed: half the particles huge, half tiny (per-tile thresholds differ strongly)
+    g.SOFT_LENGTH = np.where(np.arange(g.N) % 2 == 0, 3.0, 1e-4)
+    F = gpu_forces(g, c.x, 0, g.N - 1)
+    Fo = pyport.forces(g, c.x, 0, g.N - 1)
+    assert rel_err(F, Fo).max() < 1e-12
+
+
+def test_deterministic_and_range_split_consistent():
+    c = ic.random_sphere(5000, 21)
+    g = c.g
+    F1 = gpu_forces(g, c.x, 0, g.N - 1)
+    F2 = gpu_forces(g, c.x, 0, g.N - 1)
+    assert np.array_equal(F1, F2)  # fixed chunk order: bitwise reproducible
+    Fa = gpu_forces(g, c.x, 0, 2499)
+    Fb = gpu_forces(g, c.x, 2500, 4999)
+    assert rel_err(np.concatenate([Fa, Fb]), F1).max() < 1e-13
+
+
+def test_momentum_conservation_property():
+    c = ic.random_sphere(30000, 31, cosmology=0)
+    g = c.g
+    F = gpu_forces(g, c.x, 0, g.N - 1).reshape(-1, 3)
+    P = (g.M[:, None] * F).sum(axis=0)
+    assert np.abs(P).max() < 1e-12 * np.abs(g.M[:, None] * F).sum()
+
+
+KDK_CASES = ["kdk_r3_f64", "kdk_r3_f32", "kdk_t3_f64", "kdk_s1r2nl_f64"]
+
+
+@pytest.mark.parametrize("name", KDK_CASES)
+def test_kdk_matches_reference_step(name):
+    """device-resident KDK (Engine.step) vs the reference's own step() over the same h sequence"""
+    g, d = load_golden(name)
+    f64 = g.REAL == np.float64
+    eng = sb.Engine(g, 0)
+    eng.upload(d["x"], d["v"])
+    eng.forces()
+    h0 = eng.calculate_init_h()
+    assert math.isclose(h0, d["h_seq"][0], rel_tol=1e-11 if f64 else 1e-4)
+    for k, h in enumerate(d["h_seq"][:-1]):
+        e = eng.step(float(h))
+        assert math.isclose(e, d["errmax_seq"][k], rel_tol=1e-10 if f64 else 1e-3)
+        assert math.isclose(eng.a, d["a_seq"][k], rel_tol=1e-13)
+        assert math.isclose(eng.next_h(), d["h_seq"][k + 1], rel_tol=1e-10 if f64 else 1e-3)
+    x, v, F = eng.download()
+    eng.close()
+    nsteps = len(d["h_seq"]) - 1
+    scale = max(g.Rsim, g.L)
+    dx = np.abs(x - d["x1"]).max() / scale
+    print(f"{name}: max |dx|/R after {nsteps} steps = {dx:.3e}")
+    assert dx < (1e-12 if f64 else 1e-5) * nsteps
+    assert rel_err(F, d["F1"]).max() < (1e-11 if f64 else 1e-4)
+    assert rel_err(v, d["v1"]).max() < (1e-10 if f64 else 1e-3)
+
+
+def test_resident_engine_matches_stateless_and_upload_x():
+    c = ic.random_sphere(3000, 77)
+    g = c.g
+    F = gpu_forces(g, c.x, 0, g.N - 1)
+    eng = sb.Engine(g, 0)
+    eng.upload(c.x, c.v)
+    eng.forces(0, g.N - 1)
+    assert np.array_equal(eng.download_forces(0, g.N - 1), F)
+    x2 = c.x + 0.01
+    eng.upload_x(x2)
+    eng.forces(100, 199)
+    assert np.array_equal(eng.download_forces(100, 199), gpu_forces(g, x2, 100, 199))
+    assert eng.launch_count() > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("topo_case", ["t3", "s1r2nl", "s1r2"])
+def test_periodic_topologies_vs_oracle_midsize(topo_case):
+    if topo_case == "t3":
+        c = ic.t3_lattice(14, 61, L=30.0, is_periodic=2)
+        if not pyref.available("t3_f64"):
+            pytest.skip("T^3 table needs oracle/_ref")
+    elif topo_case == "s1r2nl":
+        c = ic.s1r2_cylinder(3000, 24, 80, 62, lookup=False, is_periodic=2, L=20.0, r_sim=60.0, d_s=10.0, r_crit=15.0)
+    else:
+        c = ic.s1r2_cylinder(3000, 24, 80, 63, lookup=True, is_periodic=2, L=20.0, r_sim=30.0, d_s=8.0, r_crit=10.0)
+    g = c.g
+    key = (g.topology, 8)
+    if pyref.available(pyref.VARIANT[key]):
+        r = pyref.Reference(pyref.VARIANT[key])
+        r.configure(g, 400)
+        r.build_tables()
+        r.export_tables(g)
+        g.mass_in_unit_sphere = r.scalars()["mass_in_unit_sphere"]
+        Fo = r.forces(c.x, 0, g.N - 1, 0)
+    else:
+        pytest.skip("tables need oracle/_ref")
+    F = gpu_forces(g, c.x, 0, g.N - 1)
+    e = rel_err(F, Fo)
+    print(f"{topo_case}: |dF|/|F| p99 {np.percentile(e, 99):.2e} max {e.max():.2e}")
+    assert np.percentile(e, 99) < TOL64
+    assert e.max() < 50 * TOL64
+
+
+def test_full_size_c2_properties():
+    """BASELINE.json configs[1]: N = 2,000,000 FP64 compactified R^3 (size-independent properties + sampled oracle rows)"""
+    c = ic.config_c2()
+    g = c.g
+    eng = sb.Engine(g, 0)
+    eng.upload(c.x, c.v)
+    eng.forces(0, g.N - 1)
+    _, _, F = eng.download(want_x=False, want_v=False)
+    ms = eng.timings()[0]
+    print(f"C2 force eval: {ms:.1f} ms, {g.N**2 / ms / 1e-3:.3e} pairs/s")
+    assert np.isfinite(F).all()
+    # (1) momentum conservation of the pair part: sum_i m_i (F_i - B x_i) = 0
+    Fp = F.reshape(-1, 3) - g.mass_in_unit_sphere * c.x.reshape(-1, 3)
+    P = (g.M[:, None] * Fp).sum(axis=0)
+    assert np.abs(P).max() < 1e-11 * np.abs(g.M[:, None] * Fp).sum()
+    # (2) sampled rows against the oracle (core, transition and outermost shell particles)
+    rows = [0, 12345, 291999, 292000, 1000000, g.N - 1]
+    for i in rows:
+        Fo = pyport.forces(g, c.x, i, i)
+        S = pyport.force_norms(g, c.x, i, i)
+        ne = noise_err(F[3 * i: 3 * i + 3], Fo, S)
+        assert ne.max() < TOL64, (i, ne)
+    # (3) a sub-range call reproduces the same rows (different chunking, same values to rounding)
+    eng.forces(500000, 500000 + 4095)
+    Fs = eng.download_forces(500000, 500000 + 4095)
+    assert rel_err(Fs, F[3 * 500000: 3 * (500000 + 4096)]).max() < 1e-11
+    eng.close()

@@ -133,6 +133,12 @@ int steps_b200_engine_kdk_step(steps_b200_engine *e, double h, double a_old, dou
 /* device timers (CUDA events on the engine's stream): milliseconds of the last force evaluation
  * (pack + pair kernels + reduce) and of the last complete kdk_step. */
 int steps_b200_engine_timings(steps_b200_engine *e, double *force_ms, double *step_ms);
+/* milliseconds of the last pair-kernel launch alone (CUDA events around it; the roofline numerator) */
+int steps_b200_engine_pair_kernel_ms(steps_b200_engine *e, double *ms_out);
+/* caller-placed CUDA events on the engine's stream (slot 0..7) and the time between two of them;
+ * elapsed_ms synchronises on slot_b.  bench.py brackets its timed region with these. */
+int steps_b200_engine_mark(steps_b200_engine *e, int slot);
+int steps_b200_engine_elapsed_ms(steps_b200_engine *e, int slot_a, int slot_b, double *ms_out);
 /* number of kernel launches issued by the engine so far (bench.py's gpu_launches) */
 long long steps_b200_engine_launch_count(steps_b200_engine *e);
 int steps_b200_engine_sync(steps_b200_engine *e);
@@ -154,6 +160,9 @@ double steps_b200_next_timestep(double acc_param, double errmax, double h_min, d
 /* FP64 / FP32 FMA-pipe microbenchmark on `device`: returns measured TFLOP/s (2 flop per FMA) --
  * the roofline denominator for this path. */
 int steps_b200_fma_peak(int device, int real_bytes, double *tflops_out, double *sm_clock_mhz_out);
+/* same kernel launched back to back for `seconds`: the sustained figure under the power cap, the
+ * denominator for a pair kernel that runs for seconds */
+int steps_b200_fma_peak_sustained(int device, int real_bytes, double seconds, double *tflops_out);
 
 #ifdef __cplusplus
 }

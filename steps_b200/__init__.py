@@ -13,6 +13,7 @@ from .api import (  # noqa: F401
     UNIT_V,
     calculate_softening_length,
     fma_peak,
+    fma_peak_sustained,
     force_entry,
     forces,
     forces_periodic,

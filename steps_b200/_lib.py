@@ -76,6 +76,9 @@ SYMBOLS = {
     "steps_b200_engine_init_errmax": (_I, [_VP, _D, _D, _PD]),
     "steps_b200_engine_kdk_step": (_I, [_VP, _D, _D, _D, _D, _D, _PD]),
     "steps_b200_engine_timings": (_I, [_VP, _PD, _PD]),
+    "steps_b200_engine_pair_kernel_ms": (_I, [_VP, _PD]),
+    "steps_b200_engine_mark": (_I, [_VP, _I]),
+    "steps_b200_engine_elapsed_ms": (_I, [_VP, _I, _I, _PD]),
     "steps_b200_engine_launch_count": (C.c_longlong, [_VP]),
     "steps_b200_engine_sync": (_I, [_VP]),
     "steps_b200_engine_launch_shape": (_I, [_VP, _I, _I, _PI]),
@@ -83,6 +86,7 @@ SYMBOLS = {
     "steps_b200_hubble": (_D, [C.POINTER(CCosmo), _D]),
     "steps_b200_next_timestep": (_D, [_D, _D, _D, _D]),
     "steps_b200_fma_peak": (_I, [_I, _I, _PD, _PD]),
+    "steps_b200_fma_peak_sustained": (_I, [_I, _I, _D, _PD]),
 }
 
 _lib = None

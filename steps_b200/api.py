@@ -211,6 +211,13 @@ def fma_peak(device: int, real_bytes: int) -> tuple:
     return tf.value, mhz.value
 
 
+def fma_peak_sustained(device: int, real_bytes: int, seconds: float = 2.0) -> float:
+    """FMA-pipe TFLOP/s of the same microbenchmark run back to back for `seconds` (power-capped clocks)"""
+    tf = C.c_double()
+    check(_lib.load().steps_b200_fma_peak_sustained(device, real_bytes, seconds, C.byref(tf)))
+    return tf.value
+
+
 class Engine:
     """Device-resident x, v, F, M, s + KDK stepping (replaces step(), step.cc:100-312).
 
@@ -309,6 +316,19 @@ class Engine:
         f, s = C.c_double(), C.c_double()
         check(self.lib.steps_b200_engine_timings(self._h, C.byref(f), C.byref(s)))
         return f.value, s.value
+
+    def pair_kernel_ms(self) -> float:
+        m = C.c_double()
+        check(self.lib.steps_b200_engine_pair_kernel_ms(self._h, C.byref(m)))
+        return m.value
+
+    def mark(self, slot: int) -> None:
+        check(self.lib.steps_b200_engine_mark(self._h, slot))
+
+    def elapsed_ms(self, slot_a: int, slot_b: int) -> float:
+        m = C.c_double()
+        check(self.lib.steps_b200_engine_elapsed_ms(self._h, slot_a, slot_b, C.byref(m)))
+        return m.value
 
     def launch_count(self) -> int:
         return int(self.lib.steps_b200_engine_launch_count(self._h))

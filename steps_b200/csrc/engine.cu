@@ -146,7 +146,8 @@ struct steps_b200_engine {
     double *d_errmax = nullptr, *h_errmax = nullptr;
     size_t fpart_bytes = 0;
     const void *h_table_src = nullptr, *h_radial_src = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // force begin/end, step begin/end, pair kernel begin/end
+    cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // caller-placed (bench)
     long long launches = 0;
     bool have_state = false;
     TopoParams tp{};
@@ -256,6 +257,7 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     a.n_tiles = pl.n_tiles;
     a.n_j = e->n;
     a.fstride = n_i;
+    CU_TRY(cudaEventRecord(e->ev[4], e->stream));
     if (tuned_f64) {
         auto kern = force_r3_f64_kernel<F64_R, F64_THREADS, F64_TJ, F64_STAGES, F64_MINB>;
         const size_t smem = (size_t)F64_STAGES * F64_TJ * sizeof(JRec64) + 2 * F64_STAGES * sizeof(uint64_t);
@@ -279,6 +281,7 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     }
     e->launches++;
     CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(e->ev[5], e->stream));
     // deterministic chunk reduction + background term
     reduce_kernel<T><<<(n_i + 255) / 256, 256, 0, e->stream>>>(static_cast<const T *>(e->d_fpart), pl.n_chunks, n_i, n_i, id_min,
                                                                 static_cast<const T *>(e->d_x), static_cast<T *>(e->d_F), e->tp);
@@ -412,6 +415,7 @@ extern "C" int steps_b200_engine_create(steps_b200_engine **out, const steps_b20
     E_TRY(cudaMemset(e->d_F, 0, 3 * n * rb));
     E_TRY(cudaMemset(e->d_v, 0, 3 * n * rb));
     for (auto &ev : e->ev) E_TRY(cudaEventCreate(&ev));
+    for (auto &ev : e->marks) E_TRY(cudaEventCreate(&ev));
 #undef E_TRY
     if (upload_tables(e)) {
         steps_b200_engine_destroy(e);
@@ -431,6 +435,8 @@ extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
         if (b) cudaFree(b);
     if (e->h_errmax) cudaFreeHost(e->h_errmax);
     for (auto &ev : e->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->marks)
         if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -573,6 +579,35 @@ extern "C" int steps_b200_engine_timings(steps_b200_engine *e, double *force_ms,
         if (cudaEventElapsedTime(&s, e->ev[2], e->ev[3]) != cudaSuccess) { cudaGetLastError(); s = -1.f; }
         *step_ms = s;
     }
+    return 0;
+}
+
+extern "C" int steps_b200_engine_pair_kernel_ms(steps_b200_engine *e, double *ms_out) {
+    if (!e || !ms_out) return fail("engine or output is NULL");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, e->ev[4], e->ev[5]) != cudaSuccess) { cudaGetLastError(); f = -1.f; }
+    *ms_out = f;
+    return 0;
+}
+
+extern "C" int steps_b200_engine_mark(steps_b200_engine *e, int slot) {
+    if (!e) return fail("engine is NULL");
+    if (slot < 0 || slot >= 8) return fail("mark slot must be 0..7");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaEventRecord(e->marks[slot], e->stream));
+    return 0;
+}
+
+extern "C" int steps_b200_engine_elapsed_ms(steps_b200_engine *e, int slot_a, int slot_b, double *ms_out) {
+    if (!e || !ms_out) return fail("engine or output is NULL");
+    if (slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8) return fail("mark slot must be 0..7");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaEventSynchronize(e->marks[slot_b]));
+    float f = 0.f;
+    CU_TRY(cudaEventElapsedTime(&f, e->marks[slot_a], e->marks[slot_b]));
+    *ms_out = f;
     return 0;
 }
 
@@ -751,6 +786,54 @@ extern "C" int steps_b200_fma_peak(int device, int real_bytes, double *tflops_ou
         const double lanes = real_bytes == 8 ? 64.0 : 128.0;
         *sm_clock_mhz_out = flops / 2.0 / (best * 1e-3) / (lanes * prop.multiProcessorCount) / 1e6;
     }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    return 0;
+}
+
+// the same microbenchmark launched back to back for `seconds`: the sustained (power-capped) figure
+// that a seconds-long pair kernel has to be compared with
+extern "C" int steps_b200_fma_peak_sustained(int device, int real_bytes, double seconds, double *tflops_out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail("no CUDA device available");
+    }
+    if (!tflops_out || !(seconds > 0.0)) return fail("bad arguments");
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    const int iters = real_bytes == 8 ? (1 << 15) : (1 << 16);
+    void *d = nullptr;
+    CU_TRY(cudaMalloc(&d, (size_t)blocks * threads * 8));
+    cudaEvent_t a, b;
+    CU_TRY(cudaEventCreate(&a));
+    CU_TRY(cudaEventCreate(&b));
+    auto launch = [&](int n) {
+        for (int r = 0; r < n; ++r) {
+            if (real_bytes == 8) fma_peak_kernel<double><<<blocks, threads>>>((double *)d, iters, 1.0000001, 1e-9);
+            else fma_peak_kernel<float><<<blocks, threads>>>((float *)d, iters, 1.0000001f, 1e-9f);
+        }
+    };
+    // calibrate one launch, then run as many as fill `seconds`
+    launch(2);
+    CU_TRY(cudaEventRecord(a));
+    launch(4);
+    CU_TRY(cudaEventRecord(b));
+    CU_TRY(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, a, b));
+    int n = (int)(seconds * 1e3 / (ms / 4.0)) + 1;
+    if (n > 20000) n = 20000;
+    CU_TRY(cudaEventRecord(a));
+    launch(n);
+    CU_TRY(cudaEventRecord(b));
+    CU_TRY(cudaEventSynchronize(b));
+    CU_TRY(cudaEventElapsedTime(&ms, a, b));
+    const double flops = 2.0 * 8.0 * iters * (double)blocks * threads * n;
+    *tflops_out = flops / (ms * 1e-3) / 1e12;
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     cudaFree(d);

@@ -51,7 +51,11 @@ def make_ic(args):
     from steps_b200 import ic
 
     if args.config == "c2":
-        c = ic.config_c2(n_total=args.n) if args.n else ic.config_c2()
+        if args.n and args.n != 2_000_000:
+            # development sizes: same geometry (122 tan-spaced shells holding 85.4 % of the particles), scaled counts
+            c = ic.compactified_r3(args.n, 224, max(1, int(0.854 * args.n / 122)), 20242, name=f"C2-shaped compactified R^3 N={args.n}")
+        else:
+            c = ic.config_c2()
     elif args.config == "c1":
         c = ic.config_c1()
     elif args.config == "c5":

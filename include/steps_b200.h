@@ -75,6 +75,17 @@ int steps_b200_forces_f64(const steps_b200_params *p, const double *x, const dou
 int steps_b200_forces_f32(const steps_b200_params *p, const float *x, const float *M, const float *soft,
                           float *F, int id_min, int id_max);
 
+/* The same call with the i-range split over n_gpu devices driven from the calling thread, starting at device
+ * $STEPS_B200_DEVICE (default 0): replaces forces_cuda(x, F, n_GPU, ID_min, ID_max) (forces_cuda.cu:878-1117),
+ * whose n_GPU OpenMP threads each own one device.  Fewer visible devices than asked: warn and clamp
+ * (forces_cuda.cu:897-907). */
+int steps_b200_forces_multi_f64(const steps_b200_params *p, const double *x, const double *M, const double *soft,
+                                double *F, int id_min, int id_max, int n_gpu);
+int steps_b200_forces_multi_f32(const steps_b200_params *p, const float *x, const float *M, const float *soft,
+                                float *F, int id_min, int id_max, int n_gpu);
+/* frees the device buffers the stateless calls cache between invocations */
+void steps_b200_release_cached(void);
+
 /* void calculate_softening_length(REAL*SOFT_LENGTH, REAL*M, int N)  utils.cc:59-82.
  * Host O(N) helper kept in the library so a caller does not need the reference's utils.o.
  * Outputs M_min and rho_part as the reference's globals of the same name. */
@@ -110,6 +121,9 @@ int steps_b200_engine_upload(steps_b200_engine *e, const void *x, const void *v,
 /* only positions (stateless-style use of a resident engine) */
 int steps_b200_engine_upload_x(steps_b200_engine *e, const void *x);
 
+/* resident forces [3N] from host (a caller that evaluated the initial forces elsewhere, main.cc:1581-1607) */
+int steps_b200_engine_upload_forces(steps_b200_engine *e, const void *F);
+
 /* forces for i in [id_min, id_max] from the resident positions into the resident F (asynchronous) */
 int steps_b200_engine_forces(steps_b200_engine *e, int id_min, int id_max);
 /* copy the resident F slice [id_min, id_max] to host (synchronises) */
@@ -144,6 +158,28 @@ long long steps_b200_engine_launch_count(steps_b200_engine *e);
 int steps_b200_engine_sync(steps_b200_engine *e);
 /* launch-shape report for DESIGN/bench: out[0]=i per CTA, out[1]=j chunks, out[2]=CTAs, out[3]=j tile */
 int steps_b200_engine_launch_shape(steps_b200_engine *e, int id_min, int id_max, int *out4);
+
+/* ------------------------------------------------------------------------------------------
+ * (2b) In-process multi-GPU group: n_gpu resident engines in ONE process (devices first_device ...),
+ *     i-partitioned, NCCL between them, one library-owned host thread per device inside every call --
+ *     the caller stays single-threaded.  This is what replaces the reference's `StePS_CUDA <param> <nGPU>`
+ *     model (one OpenMP thread per GPU, forces_cuda.cu:933-941; step.cc:122-125) for the resident path.
+ *     One-process-per-GPU callers (MPI ranks, torchrun) use steps_b200_engine_comm_init instead.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct steps_b200_group steps_b200_group;
+int steps_b200_group_create(steps_b200_group **out, const steps_b200_params *p, int real_bytes, int n_gpu, int first_device);
+void steps_b200_group_destroy(steps_b200_group *g);
+int steps_b200_group_size(steps_b200_group *g);
+steps_b200_engine *steps_b200_group_engine(steps_b200_group *g, int d);
+/* full host state to every engine; F may be NULL (then call steps_b200_group_forces) */
+int steps_b200_group_upload(steps_b200_group *g, const void *x, const void *v, const void *M, const void *soft, const void *F);
+/* every engine evaluates the forces of its own i-range (synchronises) */
+int steps_b200_group_forces(steps_b200_group *g);
+int steps_b200_group_init_errmax(steps_b200_group *g, double a, double hubble, double *errmax_out);
+int steps_b200_group_kdk_step(steps_b200_group *g, double h, double a_old, double hubble_old, double a_new, double hubble_new,
+                              double *errmax_out);
+/* gather the state to host arrays [3N]: x from the replica, v and F from each owner; any may be NULL */
+int steps_b200_group_download(steps_b200_group *g, void *x, void *v, void *F);
 
 /* ------------------------------------------------------------------------------------------
  * (3) Host scalars of the integrator, restated so a C/C++ driver needs nothing else:

@@ -25,15 +25,17 @@ class SrefConfig(C.Structure):
                 ("a_start", C.c_double)]
 
 
-def available(variant: str) -> bool:
-    return os.path.exists(os.path.join(REF_DIR, f"libsteps_ref_{variant}.so"))
+def available(variant: str, shim: bool = False) -> bool:
+    return os.path.exists(os.path.join(REF_DIR, f"libsteps_{'shim' if shim else 'ref'}_{variant}.so"))
 
 
 class Reference:
     """One loaded variant of the reference.  Not re-entrant (the reference is a bag of globals)."""
 
-    def __init__(self, variant: str):
-        path = os.path.join(REF_DIR, f"libsteps_ref_{variant}.so")
+    def __init__(self, variant: str, shim: bool = False):
+        """shim=True loads the DROP-IN build instead: the same reference TUs minus forces.cc/step.cc plus
+        steps_b200/csrc/shim/*.cc linked against libstepsb200.so (needs a GPU to compute anything)."""
+        path = os.path.join(REF_DIR, f"libsteps_{'shim' if shim else 'ref'}_{variant}.so")
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path}: build with `make -C oracle ref` (needs /root/reference)")
         self.lib = C.CDLL(path)
@@ -42,8 +44,11 @@ class Reference:
         self.REAL = np.float64 if self.real_bytes == 8 else np.float32
         self.creal = C.c_double if self.real_bytes == 8 else C.c_float
         self.topology = self.lib.sref_topology()
-        self.lib.sref_force_softening.restype = self.creal
-        self.lib.sref_force_softening.argtypes = [self.creal, self.creal]
+        self.shim = bool(self.lib.sref_is_shim())
+        assert self.shim == shim
+        if not shim:
+            self.lib.sref_force_softening.restype = self.creal
+            self.lib.sref_force_softening.argtypes = [self.creal, self.creal]
         self.lib.sref_table.restype = C.c_void_p
         self.lib.sref_kdk_begin.restype = C.c_double
         self.lib.sref_kdk_step.restype = C.c_double
@@ -113,8 +118,12 @@ class Reference:
         x = np.ascontiguousarray(x, dtype=self.REAL)
         F = np.zeros(3 * (id_max - id_min + 1), dtype=self.REAL)
         rc = self.lib.sref_forces(x.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p), id_min, id_max, nthreads)
-        assert rc == 0
+        if rc != 0:
+            raise RuntimeError("reference ForceError flag set (forces_cuda.cu:970-974 convention)")
         return F
+
+    def set_n_gpu(self, n: int) -> None:
+        self.lib.sref_set_n_gpu(n)
 
     def kdk_begin(self, x, v, nthreads: int = 0) -> float:
         x = np.ascontiguousarray(x, dtype=self.REAL)

@@ -127,8 +127,15 @@ int sref_configure(const sref_config *c)
     return 0;
 }
 
+#ifdef STEPS_SHIM_BUILD
+void steps_b200_shim_reset();   /* steps_b200_step_shim.cc */
+#endif
+
 int sref_set_particles(int n, const REAL *masses)
 {
+#ifdef STEPS_SHIM_BUILD
+    steps_b200_shim_reset();
+#endif
     if (g_alloc_n) { free(M); free(SOFT_LENGTH); free(x); free(v); free(F); }
     N = n; N_mpi_thread = n; ID_MPI_min = 0; ID_MPI_max = n - 1;
     M = (REAL *)malloc(sizeof(REAL) * n);
@@ -152,7 +159,20 @@ void sref_get_scalars(double *out4)
     out4[3] = (double)((REAL)H0 * H0 * Omega_lambda);
 }
 
+#ifndef STEPS_SHIM_BUILD
 REAL sref_force_softening(REAL r, REAL b) { return force_softening(r, b); }
+#endif
+/* 1 when forces()/step() of this library are the steps_b200 shims (drop-in build), 0 for the pure reference */
+int sref_is_shim(void)
+{
+#ifdef STEPS_SHIM_BUILD
+    return 1;
+#else
+    return 0;
+#endif
+}
+/* n_GPU of the reference (argv[2], main.cc:1186-1195): devices one process drives */
+void sref_set_n_gpu(int n) { n_GPU = n; }
 
 /* Builds the topology's lookup tables with the reference's own builders, following the call
  * sites in main.cc:412-534 (T^3), :562-726 and :1263-1310 (S^1xR^2).  Returns 0 on success. */
@@ -252,6 +272,9 @@ double sref_kdk_begin(const REAL *x0, const REAL *v0, int nthreads)
     memcpy(x, x0, sizeof(REAL) * 3 * (size_t)N);
     memcpy(v, v0, sizeof(REAL) * 3 * (size_t)N);
     N_mpi_thread = N; ID_MPI_min = 0; ID_MPI_max = N - 1;
+#ifdef STEPS_SHIM_BUILD
+    steps_b200_shim_reset();
+#endif
     a = a_start; a_tmp = a; T = 0.0;
     if (COSMOLOGY == 0) a = 1;
     if (COSMOLOGY == 1 && COMOVING_INTEGRATION == 1) Hubble_param = CALCULATE_Hubble_param(a);

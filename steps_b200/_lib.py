@@ -61,6 +61,9 @@ SYMBOLS = {
     "steps_b200_device_count": (_I, []),
     "steps_b200_forces_f64": (_I, [_PP, _VP, _VP, _VP, _VP, _I, _I]),
     "steps_b200_forces_f32": (_I, [_PP, _VP, _VP, _VP, _VP, _I, _I]),
+    "steps_b200_forces_multi_f64": (_I, [_PP, _VP, _VP, _VP, _VP, _I, _I, _I]),
+    "steps_b200_forces_multi_f32": (_I, [_PP, _VP, _VP, _VP, _VP, _I, _I, _I]),
+    "steps_b200_release_cached": (None, []),
     "steps_b200_softening_f64": (_I, [_VP, _I, _D, _VP, _PD, _PD]),
     "steps_b200_softening_f32": (_I, [_VP, _I, C.c_float, _VP, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "steps_b200_engine_create": (_I, [C.POINTER(_VP), _PP, _I, _I]),
@@ -70,6 +73,16 @@ SYMBOLS = {
     "steps_b200_engine_comm_init": (_I, [_VP, _VP, _I, _I]),
     "steps_b200_engine_upload": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "steps_b200_engine_upload_x": (_I, [_VP, _VP]),
+    "steps_b200_engine_upload_forces": (_I, [_VP, _VP]),
+    "steps_b200_group_create": (_I, [C.POINTER(_VP), _PP, _I, _I, _I]),
+    "steps_b200_group_destroy": (None, [_VP]),
+    "steps_b200_group_size": (_I, [_VP]),
+    "steps_b200_group_engine": (_VP, [_VP, _I]),
+    "steps_b200_group_upload": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "steps_b200_group_forces": (_I, [_VP]),
+    "steps_b200_group_init_errmax": (_I, [_VP, _D, _D, _PD]),
+    "steps_b200_group_kdk_step": (_I, [_VP, _D, _D, _D, _D, _D, _PD]),
+    "steps_b200_group_download": (_I, [_VP, _VP, _VP, _VP]),
     "steps_b200_engine_forces": (_I, [_VP, _I, _I]),
     "steps_b200_engine_download_forces": (_I, [_VP, _VP, _I, _I]),
     "steps_b200_engine_download": (_I, [_VP, _VP, _VP, _VP]),

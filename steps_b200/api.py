@@ -65,6 +65,7 @@ class Globals:
     Nz_EWALD_FORCE_GRID: int = 0
     RADIAL_FORCE_TABLE: Optional[np.ndarray] = None
     ForceError: bool = False
+    n_GPU: int = 1  # devices driven by one call (the reference's argv[2], main.cc:1186-1195)
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -159,8 +160,12 @@ def _forces_any(g: Globals, topo_ok: tuple, x: np.ndarray, F: np.ndarray, ID_min
     M = _arr(g.M, g, g.N, "M")
     s = _arr(g.SOFT_LENGTH, g, g.N, "SOFT_LENGTH")
     p = g.cparams()
-    fn = lib.steps_b200_forces_f64 if g.REAL == np.float64 else lib.steps_b200_forces_f32
-    rc = fn(C.byref(p), x.ctypes.data, M.ctypes.data, s.ctypes.data, F.ctypes.data, ID_min, ID_max)
+    if g.n_GPU > 1:
+        fn = lib.steps_b200_forces_multi_f64 if g.REAL == np.float64 else lib.steps_b200_forces_multi_f32
+        rc = fn(C.byref(p), x.ctypes.data, M.ctypes.data, s.ctypes.data, F.ctypes.data, ID_min, ID_max, g.n_GPU)
+    else:
+        fn = lib.steps_b200_forces_f64 if g.REAL == np.float64 else lib.steps_b200_forces_f32
+        rc = fn(C.byref(p), x.ctypes.data, M.ctypes.data, s.ctypes.data, F.ctypes.data, ID_min, ID_max)
     if rc != 0:
         g.ForceError = True  # reference convention: forces_cuda.cu:970-974 + main.cc:1851-1856
         check(rc)

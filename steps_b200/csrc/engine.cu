@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 #include <dlfcn.h>
 #include <cuda_runtime.h>
@@ -145,7 +146,7 @@ struct steps_b200_engine {
     void *d_jrec = nullptr, *d_smax = nullptr, *d_fpart = nullptr, *d_table = nullptr, *d_radial = nullptr;
     double *d_errmax = nullptr, *h_errmax = nullptr;
     size_t fpart_bytes = 0;
-    const void *h_table_src = nullptr, *h_radial_src = nullptr;
+    size_t table_bytes = 0, radial_bytes = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // force begin/end, step begin/end, pair kernel begin/end
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // caller-placed (bench)
     long long launches = 0;
@@ -213,21 +214,32 @@ void fill_topo(steps_b200_engine *e) {
     t.radial = e->d_radial;
 }
 
+// Tables are HOST pointers owned by the caller.  A resident engine uploads them once (create); the stateless
+// entry points re-upload on every call, as the reference does (forces_cuda.cu:1015-1050): a caller may hand in a
+// different table at the same address, so pointer identity proves nothing.  Device allocations are reused.
 int upload_tables(steps_b200_engine *e) {
     const steps_b200_params &p = e->p;
     const size_t ne = table_elems(p);
     const bool need_table = ne > 0 && p.is_periodic >= 2 && p.ewald_table;
-    if (need_table && p.ewald_table != e->h_table_src) {
-        if (e->d_table) CU_TRY(cudaFree(e->d_table));
-        CU_TRY(cudaMalloc(&e->d_table, ne * e->real_bytes));
-        CU_TRY(cudaMemcpy(e->d_table, p.ewald_table, ne * e->real_bytes, cudaMemcpyHostToDevice));
-        e->h_table_src = p.ewald_table;
+    if (need_table) {
+        const size_t bytes = ne * e->real_bytes;
+        if (bytes != e->table_bytes) {
+            if (e->d_table) CU_TRY(cudaFree(e->d_table));
+            e->d_table = nullptr;
+            CU_TRY(cudaMalloc(&e->d_table, bytes));
+            e->table_bytes = bytes;
+        }
+        CU_TRY(cudaMemcpyAsync(e->d_table, p.ewald_table, bytes, cudaMemcpyHostToDevice, e->stream));
     }
-    if (p.radial_table && p.radial_table_size > 0 && p.radial_table != e->h_radial_src) {
-        if (e->d_radial) CU_TRY(cudaFree(e->d_radial));
-        CU_TRY(cudaMalloc(&e->d_radial, (size_t)p.radial_table_size * e->real_bytes));
-        CU_TRY(cudaMemcpy(e->d_radial, p.radial_table, (size_t)p.radial_table_size * e->real_bytes, cudaMemcpyHostToDevice));
-        e->h_radial_src = p.radial_table;
+    if (p.radial_table && p.radial_table_size > 0) {
+        const size_t bytes = (size_t)p.radial_table_size * e->real_bytes;
+        if (bytes != e->radial_bytes) {
+            if (e->d_radial) CU_TRY(cudaFree(e->d_radial));
+            e->d_radial = nullptr;
+            CU_TRY(cudaMalloc(&e->d_radial, bytes));
+            e->radial_bytes = bytes;
+        }
+        CU_TRY(cudaMemcpyAsync(e->d_radial, p.radial_table, bytes, cudaMemcpyHostToDevice, e->stream));
     }
     fill_topo(e);
     return 0;
@@ -494,6 +506,14 @@ extern "C" int steps_b200_engine_upload_x(steps_b200_engine *e, const void *x) {
     return 0;
 }
 
+extern "C" int steps_b200_engine_upload_forces(steps_b200_engine *e, const void *F) {
+    if (!e) return fail("engine is NULL");
+    if (!F) return fail("F is NULL");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaMemcpyAsync(e->d_F, F, 3 * (size_t)e->n * e->real_bytes, cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+
 extern "C" int steps_b200_engine_forces(steps_b200_engine *e, int id_min, int id_max) {
     if (!e) return fail("engine is NULL");
     return forces_impl(e, id_min, id_max);
@@ -635,44 +655,232 @@ extern "C" int steps_b200_engine_launch_shape(steps_b200_engine *e, int id_min, 
 
 // ------------------------------------------------------------------------------------------------ stateless path
 namespace {
-steps_b200_engine *g_cached[2] = {nullptr, nullptr};
+constexpr int MAX_DEV = 16;
+steps_b200_engine *g_cached[2][MAX_DEV] = {};
 
 bool same_shape(const steps_b200_params &a, const steps_b200_params &b) {
     return a.topology == b.topology && a.n == b.n && a.table_dim0 == b.table_dim0 && a.table_dim1 == b.table_dim1 &&
            a.radial_table_size == b.radial_table_size;
 }
 
+// One engine per device, cached between calls; the i-range is split over the devices (every GPU holds the full
+// j replica, as forces_cuda.cu:933-951 does) and all devices run concurrently, driven from this one host thread.
 int forces_stateless(const steps_b200_params *p, int real_bytes, const void *x, const void *M, const void *soft, void *F, int id_min,
-                     int id_max) {
+                     int id_max, int n_gpu, int first_device) {
     if (check_params(p)) return 1;
     if (!x || !M || !soft || !F) return fail("x, M, soft, F must be non-NULL");
     if (id_min < 0 || id_max >= p->n || id_max < id_min) return fail("bad [id_min, id_max]");
-    steps_b200_engine *&e = g_cached[real_bytes == 8 ? 0 : 1];
-    if (e && !same_shape(e->p, *p)) {
-        steps_b200_engine_destroy(e);
-        e = nullptr;
+    int ndev = steps_b200_device_count();
+    if (ndev == 0) return fail("no CUDA device available: libstepsb200 has no CPU fallback");
+    if (n_gpu < 1) return fail("n_gpu must be >= 1");
+    if (first_device < 0 || first_device >= ndev) return fail("bad device ordinal");
+    if (first_device + n_gpu > ndev) {
+        // reference behaviour (forces_cuda.cu:897-907): warn and clamp
+        fprintf(stderr, "steps_b200: %d GPU(s) requested from device %d but only %d visible; using %d\n", n_gpu, first_device, ndev,
+                ndev - first_device);
+        n_gpu = ndev - first_device;
     }
-    if (!e) {
-        int dev = 0;
-        if (const char *s = getenv("STEPS_B200_DEVICE")) dev = atoi(s);
-        if (steps_b200_engine_create(&e, p, real_bytes, dev)) return 1;
-    } else {
-        e->p = *p;
-        if (upload_tables(e)) return 1;
+    if (n_gpu > MAX_DEV) n_gpu = MAX_DEV;
+    const int n_i = id_max - id_min + 1;
+    if (n_gpu > n_i) n_gpu = n_i;
+    const int pi = real_bytes == 8 ? 0 : 1;
+    int lo[MAX_DEV], hi[MAX_DEV];
+    for (int d = 0; d < n_gpu; ++d) {
+        steps_b200_partition(n_i, n_gpu, d, &lo[d], &hi[d]);
+        lo[d] += id_min;
+        hi[d] += id_min;  // exclusive
+        steps_b200_engine *&e = g_cached[pi][first_device + d];
+        if (e && !same_shape(e->p, *p)) {
+            steps_b200_engine_destroy(e);
+            e = nullptr;
+        }
+        if (!e) {
+            if (steps_b200_engine_create(&e, p, real_bytes, first_device + d)) return 1;
+        } else {
+            e->p = *p;
+            if (upload_tables(e)) return 1;
+        }
+        if (steps_b200_engine_upload(e, x, nullptr, M, soft)) return 1;
+        if (forces_impl(e, lo[d], hi[d] - 1)) return 1;
+        CU_TRY(cudaMemcpyAsync(static_cast<char *>(F) + 3 * (size_t)(lo[d] - id_min) * real_bytes,
+                               static_cast<char *>(e->d_F) + 3 * (size_t)lo[d] * real_bytes, 3 * (size_t)(hi[d] - lo[d]) * real_bytes,
+                               cudaMemcpyDeviceToHost, e->stream));
     }
-    if (steps_b200_engine_upload(e, x, nullptr, M, soft)) return 1;
-    if (forces_impl(e, id_min, id_max)) return 1;
-    return steps_b200_engine_download_forces(e, F, id_min, id_max);
+    for (int d = 0; d < n_gpu; ++d) {
+        steps_b200_engine *e = g_cached[pi][first_device + d];
+        CU_TRY(cudaSetDevice(e->device));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return 0;
+}
+
+int env_device() {
+    const char *s = getenv("STEPS_B200_DEVICE");
+    return s ? atoi(s) : 0;
 }
 }  // namespace
 
 extern "C" int steps_b200_forces_f64(const steps_b200_params *p, const double *x, const double *M, const double *soft, double *F,
                                      int id_min, int id_max) {
-    return forces_stateless(p, 8, x, M, soft, F, id_min, id_max);
+    return forces_stateless(p, 8, x, M, soft, F, id_min, id_max, 1, env_device());
 }
 extern "C" int steps_b200_forces_f32(const steps_b200_params *p, const float *x, const float *M, const float *soft, float *F, int id_min,
                                      int id_max) {
-    return forces_stateless(p, 4, x, M, soft, F, id_min, id_max);
+    return forces_stateless(p, 4, x, M, soft, F, id_min, id_max, 1, env_device());
+}
+extern "C" int steps_b200_forces_multi_f64(const steps_b200_params *p, const double *x, const double *M, const double *soft, double *F,
+                                           int id_min, int id_max, int n_gpu) {
+    return forces_stateless(p, 8, x, M, soft, F, id_min, id_max, n_gpu, env_device());
+}
+extern "C" int steps_b200_forces_multi_f32(const steps_b200_params *p, const float *x, const float *M, const float *soft, float *F,
+                                           int id_min, int id_max, int n_gpu) {
+    return forces_stateless(p, 4, x, M, soft, F, id_min, id_max, n_gpu, env_device());
+}
+extern "C" void steps_b200_release_cached(void) {
+    for (auto &row : g_cached)
+        for (auto &e : row)
+            if (e) {
+                steps_b200_engine_destroy(e);
+                e = nullptr;
+            }
+}
+
+// ------------------------------------------------------------------------------------------------ in-process multi-GPU group
+// n engines in ONE process, one library-owned host thread per device for every collective phase (the
+// reference's model: one OpenMP thread per GPU, forces_cuda.cu:933-941) -- the caller stays single-threaded.
+struct steps_b200_group {
+    std::vector<steps_b200_engine *> eng;
+    int n = 0, real_bytes = 8;
+};
+
+namespace {
+// run fn(d) for every engine on its own thread; first error message wins
+template <typename Fn>
+int group_parallel(steps_b200_group *g, Fn fn) {
+    const int n = (int)g->eng.size();
+    std::vector<int> rc(n, 0);
+    std::vector<std::string> msg(n);
+    auto body = [&](int d) {
+        rc[d] = fn(d);
+        if (rc[d]) msg[d] = g_err;  // g_err is thread_local
+    };
+    if (n == 1) {
+        body(0);
+    } else {
+        std::vector<std::thread> th;
+        th.reserve(n);
+        for (int d = 0; d < n; ++d) th.emplace_back(body, d);
+        for (auto &t : th) t.join();
+    }
+    for (int d = 0; d < n; ++d)
+        if (rc[d]) return fail("device " + std::to_string(g->eng[d]->device) + ": " + msg[d]);
+    return 0;
+}
+}  // namespace
+
+extern "C" void steps_b200_group_destroy(steps_b200_group *g) {
+    if (!g) return;
+    for (auto *e : g->eng) steps_b200_engine_destroy(e);
+    delete g;
+}
+
+extern "C" int steps_b200_group_create(steps_b200_group **out, const steps_b200_params *p, int real_bytes, int n_gpu, int first_device) {
+    if (!out) return fail("out is NULL");
+    *out = nullptr;
+    if (check_params(p)) return 1;
+    const int ndev = steps_b200_device_count();
+    if (ndev == 0) return fail("no CUDA device available: libstepsb200 has no CPU fallback");
+    if (n_gpu < 1 || first_device < 0 || first_device >= ndev) return fail("bad n_gpu / first_device");
+    if (first_device + n_gpu > ndev) {
+        fprintf(stderr, "steps_b200: %d GPU(s) requested from device %d but only %d visible; using %d\n", n_gpu, first_device, ndev,
+                ndev - first_device);
+        n_gpu = ndev - first_device;
+    }
+    if (n_gpu > p->n) n_gpu = p->n;
+    auto *g = new steps_b200_group();
+    g->n = p->n;
+    g->real_bytes = real_bytes;
+    for (int d = 0; d < n_gpu; ++d) {
+        steps_b200_engine *e = nullptr;
+        if (steps_b200_engine_create(&e, p, real_bytes, first_device + d)) {
+            steps_b200_group_destroy(g);
+            return 1;
+        }
+        g->eng.push_back(e);
+    }
+    if (n_gpu > 1) {
+        unsigned char id[128];
+        if (steps_b200_nccl_unique_id(id)) {
+            steps_b200_group_destroy(g);
+            return 1;
+        }
+        if (group_parallel(g, [&](int d) { return steps_b200_engine_comm_init(g->eng[d], id, d, n_gpu); })) {
+            steps_b200_group_destroy(g);
+            return 1;
+        }
+    }
+    *out = g;
+    return 0;
+}
+
+extern "C" int steps_b200_group_size(steps_b200_group *g) { return g ? (int)g->eng.size() : 0; }
+extern "C" steps_b200_engine *steps_b200_group_engine(steps_b200_group *g, int d) {
+    return (g && d >= 0 && d < (int)g->eng.size()) ? g->eng[d] : nullptr;
+}
+
+extern "C" int steps_b200_group_upload(steps_b200_group *g, const void *x, const void *v, const void *M, const void *soft, const void *F) {
+    if (!g) return fail("group is NULL");
+    for (auto *e : g->eng) {
+        if (steps_b200_engine_upload(e, x, v, M, soft)) return 1;
+        if (F && steps_b200_engine_upload_forces(e, F)) return 1;
+    }
+    for (auto *e : g->eng)
+        if (steps_b200_engine_sync(e)) return 1;
+    return 0;
+}
+
+extern "C" int steps_b200_group_forces(steps_b200_group *g) {
+    if (!g) return fail("group is NULL");
+    for (auto *e : g->eng)
+        if (forces_impl(e, e->i_lo, e->i_hi - 1)) return 1;
+    for (auto *e : g->eng)
+        if (steps_b200_engine_sync(e)) return 1;
+    return 0;
+}
+
+extern "C" int steps_b200_group_init_errmax(steps_b200_group *g, double a, double hubble, double *errmax_out) {
+    if (!g || !errmax_out) return fail("group or output is NULL");
+    std::vector<double> em(g->eng.size(), 0.0);
+    if (group_parallel(g, [&](int d) { return steps_b200_engine_init_errmax(g->eng[d], a, hubble, &em[d]); })) return 1;
+    *errmax_out = em[0];  // identical on every engine after the max all-reduce
+    return 0;
+}
+
+extern "C" int steps_b200_group_kdk_step(steps_b200_group *g, double h, double a_old, double hubble_old, double a_new, double hubble_new,
+                                         double *errmax_out) {
+    if (!g || !errmax_out) return fail("group or output is NULL");
+    std::vector<double> em(g->eng.size(), 0.0);
+    if (group_parallel(g, [&](int d) { return steps_b200_engine_kdk_step(g->eng[d], h, a_old, hubble_old, a_new, hubble_new, &em[d]); }))
+        return 1;
+    *errmax_out = em[0];
+    return 0;
+}
+
+// x: full (every engine holds the gathered replica -- taken from engine 0); v, F: each engine's owned rows
+extern "C" int steps_b200_group_download(steps_b200_group *g, void *x, void *v, void *F) {
+    if (!g) return fail("group is NULL");
+    const size_t rb = g->real_bytes;
+    for (size_t d = 0; d < g->eng.size(); ++d) {
+        steps_b200_engine *e = g->eng[d];
+        CU_TRY(cudaSetDevice(e->device));
+        if (x && d == 0) CU_TRY(cudaMemcpyAsync(x, e->d_x, 3 * (size_t)e->n * rb, cudaMemcpyDeviceToHost, e->stream));
+        const size_t off = 3 * (size_t)e->i_lo * rb, len = 3 * (size_t)(e->i_hi - e->i_lo) * rb;
+        if (v) CU_TRY(cudaMemcpyAsync(static_cast<char *>(v) + off, static_cast<char *>(e->d_v) + off, len, cudaMemcpyDeviceToHost, e->stream));
+        if (F) CU_TRY(cudaMemcpyAsync(static_cast<char *>(F) + off, static_cast<char *>(e->d_F) + off, len, cudaMemcpyDeviceToHost, e->stream));
+    }
+    for (auto *e : g->eng)
+        if (steps_b200_engine_sync(e)) return 1;
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ host helpers

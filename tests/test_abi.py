@@ -123,3 +123,25 @@ def test_ic_shapes():
     assert math.isclose(t.g.M.sum() / t.g.L**3, t.g.rho_crit * t.g.Omega_m, rel_tol=1e-12)
     s = ic.s1r2_cylinder(4096, 24, 100, 4)
     assert s.x[2::3].min() >= 0 and s.x[2::3].max() < s.g.L
+
+
+def test_dropin_shim_exports_the_reference_symbols_and_fails_loudly_without_gpu():
+    """The drop-in build (reference TUs minus forces.cc/step.cc plus steps_b200/csrc/shim/*.cc) must define the
+    reference's C++-mangled entry points and, without a GPU, set ForceError instead of computing."""
+    import subprocess
+
+    from oracle import pyref
+
+    if not pyref.available("r3_f64", shim=True):
+        pytest.skip("oracle/_ref shim build needs /root/reference")
+    path = os.path.join(pyref.REF_DIR, "libsteps_shim_r3_f64.so")
+    syms = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    for mangled in ("_Z6forcesPdS_ii", "_Z21recalculate_softeningv", "_Z4stepPdS_S_", "_Z16calculate_init_hv"):
+        assert mangled in syms, mangled
+    if _lib.load().steps_b200_device_count() > 0:
+        return
+    c = ic.random_sphere(128, 3)
+    r = pyref.Reference("r3_f64", shim=True)
+    r.configure(c.g)
+    with pytest.raises(RuntimeError, match="ForceError"):
+        r.forces(c.x, 0, 127)

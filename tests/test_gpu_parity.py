@@ -252,3 +252,53 @@ def test_full_size_c2_properties():
     Fs = eng.download_forces(500000, 500000 + 4095)
     assert rel_err(Fs, F[3 * 500000: 3 * (500000 + 4096)]).max() < 1e-11
     eng.close()
+
+
+# ---------------------------------------------------------------- the drop-in boundary
+SHIM_FORCE_CASES = [("r3_f64_comoving", "r3_f64"), ("r3_f32_comoving", "r3_f32"), ("r3_f64_zoom", "r3_f64"), ("t3_f64_ewald", "t3_f64"),
+                    ("s1r2nl_f64_images", "s1r2nl_f64"), ("s1r2_f64_lookup", "s1r2_f64")]
+
+
+@pytest.mark.parametrize("name,variant", SHIM_FORCE_CASES)
+def test_dropin_forces_shim_inside_reference_build(name, variant):
+    """reference main.cc globals + reference table builders + OUR forces() TU (steps_b200_forces_shim.cc)
+    reproduce the golden forces of the unmodified reference"""
+    if not pyref.available(variant, shim=True):
+        pytest.skip("oracle/_ref shim build not present")
+    g, d = load_golden(name)
+    r = pyref.Reference(variant, shim=True)
+    r.configure(g)
+    r.build_tables()  # the reference's own builders fill its own globals; the shim packs them on every call
+    F = r.forces(d["x"], 0, g.N - 1)
+    e = rel_err(F, d["F"])
+    print(f"shim {name}: max |dF|/|F| = {e.max():.3e}")
+    assert e.max() < tol(g)
+    lo, hi = int(d["sub_lo"]), int(d["sub_hi"])
+    assert rel_err(r.forces(d["x"], lo, hi), d["Fsub"]).max() < tol(g)
+
+
+@pytest.mark.parametrize("name,variant", [("kdk_r3_f64", "r3_f64"), ("kdk_r3_f32", "r3_f32"), ("kdk_t3_f64", "t3_f64"),
+                                          ("kdk_s1r2nl_f64", "s1r2nl_f64")])
+def test_dropin_step_shim_inside_reference_build(name, variant):
+    """reference globals + OUR step()/calculate_init_h() TU (device-resident KDK) against the reference's own step()"""
+    if not pyref.available(variant, shim=True):
+        pytest.skip("oracle/_ref shim build not present")
+    g, d = load_golden(name)
+    f64 = g.REAL == np.float64
+    r = pyref.Reference(variant, shim=True)
+    r.configure(g)
+    r.build_tables()
+    h0 = r.kdk_begin(d["x"], d["v"])
+    assert math.isclose(h0, d["h_seq"][0], rel_tol=1e-11 if f64 else 1e-4)
+    for k, h in enumerate(d["h_seq"][:-1]):
+        hn, s = r.kdk_step(float(h))
+        assert math.isclose(s["errmax"], d["errmax_seq"][k], rel_tol=1e-10 if f64 else 1e-3)
+        assert math.isclose(s["a"], d["a_seq"][k], rel_tol=1e-13)
+        assert math.isclose(hn, d["h_seq"][k + 1], rel_tol=1e-10 if f64 else 1e-3)
+    x, v, F = r.kdk_state()
+    nsteps = len(d["h_seq"]) - 1
+    dx = np.abs(x - d["x1"]).max() / max(g.Rsim, g.L)
+    print(f"shim {name}: max |dx|/R after {nsteps} steps = {dx:.3e}")
+    assert dx < (1e-12 if f64 else 1e-5) * nsteps
+    assert rel_err(F, d["F1"]).max() < (1e-11 if f64 else 1e-4)
+    assert rel_err(v, d["v1"]).max() < (1e-10 if f64 else 1e-3)

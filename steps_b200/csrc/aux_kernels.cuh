@@ -18,20 +18,65 @@ __global__ void tile_smax_kernel(const T *__restrict__ s, int n, int tj, int n_t
 }
 
 // AoS positions + masses + softenings -> staged j-records (padded to whole tiles with massless,
-// far-away records so that the tuned kernels need no bounds checks in the pair loop)
-__global__ void pack_kernel_f64(const double *__restrict__ x, const double *__restrict__ m, const double *__restrict__ s,
-                                const double *__restrict__ smax_tile, JRec64 *__restrict__ out, int n, int n_pad, int tj) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_pad) return;
+// far-away records so that the tuned kernels need no bounds checks in the pair loop), plus one
+// TileInfo64 per tile: bounding box and radial range of the tile's REAL particles, which lets a warp
+// prove "every pair of my i-particles with this tile is farther apart than any s_i + s_j" and take the
+// check-free pair loop.  One CTA of TJ threads per tile.
+template <int TJ_>
+__global__ void __launch_bounds__(TJ_) pack_kernel_f64(const double *__restrict__ x, const double *__restrict__ m, const double *__restrict__ s,
+                                                        const double *__restrict__ smax_tile, JRec64 *__restrict__ out,
+                                                        TileInfo64 *__restrict__ tinfo, int n) {
+    const int t = blockIdx.x;
+    const int j = t * TJ_ + threadIdx.x;
     JRec64 r;
-    const double sm = smax_tile[j / tj];
+    const double sm = smax_tile[t];
+    double lo[3], hi[3], rlo, rhi;
     if (j < n) {
         r.x = x[3 * (size_t)j]; r.y = x[3 * (size_t)j + 1]; r.z = x[3 * (size_t)j + 2];
         r.m = m[j]; r.m15 = 1.5 * r.m; r.m1875 = 1.875 * r.m; r.s = s[j]; r.smax = sm;
+        lo[0] = hi[0] = r.x; lo[1] = hi[1] = r.y; lo[2] = hi[2] = r.z;
+        rlo = rhi = sqrt(r.x * r.x + r.y * r.y + r.z * r.z);
     } else {
         r.x = r.y = r.z = 1.0e20; r.m = r.m15 = r.m1875 = 0.0; r.s = 0.0; r.smax = sm;
+        lo[0] = lo[1] = lo[2] = rlo = 1.0e300;
+        hi[0] = hi[1] = hi[2] = -1.0e300;
+        rhi = 0.0;
     }
     out[j] = r;
+    // block reduction: 7 mins/maxes over TJ_ threads
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        rlo = fmin(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
+        rhi = fmax(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
+    }
+    __shared__ double red[TJ_ / 32][8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        red[w][0] = lo[0]; red[w][1] = lo[1]; red[w][2] = lo[2];
+        red[w][3] = hi[0]; red[w][4] = hi[1]; red[w][5] = hi[2];
+        red[w][6] = rlo; red[w][7] = rhi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        TileInfo64 ti;
+        ti.lo[0] = red[0][0]; ti.lo[1] = red[0][1]; ti.lo[2] = red[0][2];
+        ti.hi[0] = red[0][3]; ti.hi[1] = red[0][4]; ti.hi[2] = red[0][5];
+        ti.rlo = red[0][6]; ti.rhi = red[0][7];
+        for (int q = 1; q < TJ_ / 32; ++q) {
+            for (int k = 0; k < 3; ++k) {
+                ti.lo[k] = fmin(ti.lo[k], red[q][k]);
+                ti.hi[k] = fmax(ti.hi[k], red[q][3 + k]);
+            }
+            ti.rlo = fmin(ti.rlo, red[q][6]);
+            ti.rhi = fmax(ti.rhi, red[q][7]);
+        }
+        tinfo[t] = ti;
+    }
 }
 
 __global__ void pack_kernel_f32(const float *__restrict__ x, const float *__restrict__ m, const float *__restrict__ s,

@@ -91,8 +91,40 @@ int nccl_load() {
 
 // ------------------------------------------------------------------------------------------------ launch planning
 namespace {
-// tuned R^3 FP64 kernel shape
-constexpr int F64_R = 4, F64_THREADS = 256, F64_TJ = 128, F64_STAGES = 3, F64_MINB = 2;
+// tuned R^3 FP64 kernel shapes: {i-particles per thread, threads per CTA, resident CTAs per SM, j unroll}.
+// Variant 0 is the production shape; the others exist for on-device tuning (STEPS_B200_F64_VARIANT=k).
+constexpr int F64_TJ = 128, F64_STAGES = 3;
+struct F64Variant {
+    int R, threads, minb, unroll, experiment;
+};
+constexpr F64Variant F64_VARIANTS[] = {
+    {8, 128, 2, 1},  // 0: PRODUCTION.  255 regs, 8 warps/SM
+    {4, 256, 2, 2},  // 1: 128 regs, 16 warps/SM
+    {4, 128, 4, 4},  // 2
+    {4, 128, 5, 2},  // 3: <=102 regs, 20 warps/SM
+    {2, 128, 8, 4},  // 4: <=64 regs, 32 warps/SM
+    {3, 128, 6, 2},  // 5: <=85 regs, 24 warps/SM
+    {4, 128, 4, 2},  // 6
+    {8, 128, 2, 2},  // 7
+    {6, 128, 3, 2},  // 8: <=170 regs, 12 warps/SM
+    {6, 128, 3, 1},  // 9
+    {8, 64, 4, 1},   // 10: 255 regs, 8 warps/SM in 64-thread CTAs
+    {5, 128, 3, 2},  // 11
+    {8, 128, 2, 1, 1},  // 12: TIMING EXPERIMENT: every tile takes the far loop (wrong forces for r < beta)
+    {8, 128, 2, 1, 2},  // 13: TIMING EXPERIMENT: every tile takes the checked loop (correct, slower)
+    {4, 256, 2, 2, 1},  // 14: TIMING EXPERIMENT (far only)
+    {4, 256, 2, 2, 2},  // 15: TIMING EXPERIMENT (checked only)
+};
+constexpr int N_F64_VARIANTS = sizeof(F64_VARIANTS) / sizeof(F64_VARIANTS[0]);
+int f64_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("STEPS_B200_F64_VARIANT");
+        v = s ? atoi(s) : 0;
+        if (v < 0 || v >= N_F64_VARIANTS) v = 0;
+    }
+    return v;
+}
 // exact-branch kernels
 constexpr int GEN_R = 2, GEN_THREADS = 128, GEN_TJ = 128, GEN_STAGES = 3;
 constexpr int TJ = 128;  // j-tile (records) shared by all kernels so that one packed array serves all
@@ -143,6 +175,7 @@ struct steps_b200_engine {
     ncclComm_t comm = nullptr;
     cudaStream_t stream = nullptr;
     void *d_x = nullptr, *d_v = nullptr, *d_F = nullptr, *d_m = nullptr, *d_s = nullptr;
+    void *d_tinfo = nullptr;
     void *d_jrec = nullptr, *d_smax = nullptr, *d_fpart = nullptr, *d_table = nullptr, *d_radial = nullptr;
     double *d_errmax = nullptr, *h_errmax = nullptr;
     size_t fpart_bytes = 0;
@@ -249,8 +282,9 @@ template <typename T>
 int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     using JRec = typename JRecOf<T>::type;
     const bool tuned_f64 = (sizeof(T) == 8 && e->p.topology == STEPS_TOPO_R3);
-    const int ib = tuned_f64 ? F64_R * F64_THREADS : GEN_R * GEN_THREADS;
-    const int slots = e->num_sms * (tuned_f64 ? F64_MINB : 4);
+    const F64Variant fv = F64_VARIANTS[f64_variant()];
+    const int ib = tuned_f64 ? fv.R * fv.threads : GEN_R * GEN_THREADS;
+    const int slots = e->num_sms * (tuned_f64 ? fv.minb : 4);
     Plan pl = make_plan(n_i, e->n, ib, slots, sizeof(T));
     plan_out = pl;
     const size_t need = (size_t)pl.n_chunks * 3 * (size_t)n_i * sizeof(T);
@@ -261,6 +295,7 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     }
     R3LaunchArgs a{};
     a.jrec = e->d_jrec;
+    a.tinfo = e->d_tinfo;
     a.fpart = e->d_fpart;
     a.id_min = id_min;
     a.n_i = n_i;
@@ -271,10 +306,20 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     a.fstride = n_i;
     CU_TRY(cudaEventRecord(e->ev[4], e->stream));
     if (tuned_f64) {
-        auto kern = force_r3_f64_kernel<F64_R, F64_THREADS, F64_TJ, F64_STAGES, F64_MINB>;
-        const size_t smem = (size_t)F64_STAGES * F64_TJ * sizeof(JRec64) + 2 * F64_STAGES * sizeof(uint64_t);
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<pl.ctas, F64_THREADS, smem, e->stream>>>(a);
+        const size_t smem = (size_t)F64_STAGES * (F64_TJ * sizeof(JRec64) + sizeof(TileInfo64)) + (size_t)(fv.threads / 32) * sizeof(WarpBounds64) +
+                            2 * F64_STAGES * sizeof(uint64_t);
+#define LAUNCH_F64(K)                                                                                                       \
+    case K: {                                                                                                               \
+        auto kern = force_r3_f64_kernel<F64_VARIANTS[K].R, F64_VARIANTS[K].threads, F64_TJ, F64_STAGES, F64_VARIANTS[K].minb, \
+                                        F64_VARIANTS[K].unroll, F64_VARIANTS[K].experiment>;                                                            \
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
+        kern<<<pl.ctas, F64_VARIANTS[K].threads, smem, e->stream>>>(a);                                                     \
+    } break;
+        switch (f64_variant()) {
+            LAUNCH_F64(0) LAUNCH_F64(1) LAUNCH_F64(2) LAUNCH_F64(3) LAUNCH_F64(4) LAUNCH_F64(5) LAUNCH_F64(6) LAUNCH_F64(7)
+            LAUNCH_F64(8) LAUNCH_F64(9) LAUNCH_F64(10) LAUNCH_F64(11) LAUNCH_F64(12) LAUNCH_F64(13) LAUNCH_F64(14) LAUNCH_F64(15)
+        }
+#undef LAUNCH_F64
     } else {
         const size_t smem = (size_t)GEN_STAGES * GEN_TJ * sizeof(JRec) + 2 * GEN_STAGES * sizeof(uint64_t);
 #define LAUNCH_GEN(TOPO)                                                                                  \
@@ -305,8 +350,8 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
 int pack(steps_b200_engine *e) {
     const int blocks = (e->n_pad + 255) / 256;
     if (e->real_bytes == 8)
-        pack_kernel_f64<<<blocks, 256, 0, e->stream>>>((const double *)e->d_x, (const double *)e->d_m, (const double *)e->d_s,
-                                                       (const double *)e->d_smax, (JRec64 *)e->d_jrec, e->n, e->n_pad, TJ);
+        pack_kernel_f64<TJ><<<e->n_tiles, TJ, 0, e->stream>>>((const double *)e->d_x, (const double *)e->d_m, (const double *)e->d_s,
+                                                              (const double *)e->d_smax, (JRec64 *)e->d_jrec, (TileInfo64 *)e->d_tinfo, e->n);
     else
         pack_kernel_f32<<<blocks, 256, 0, e->stream>>>((const float *)e->d_x, (const float *)e->d_m, (const float *)e->d_s,
                                                        (const float *)e->d_smax, (JRec32 *)e->d_jrec, e->n, e->n_pad, TJ);
@@ -422,6 +467,7 @@ extern "C" int steps_b200_engine_create(steps_b200_engine **out, const steps_b20
     E_TRY(cudaMalloc(&e->d_s, n * rb));
     E_TRY(cudaMalloc(&e->d_smax, (size_t)e->n_tiles * rb));
     E_TRY(cudaMalloc(&e->d_jrec, jrec_bytes));
+    E_TRY(cudaMalloc(&e->d_tinfo, (size_t)e->n_tiles * sizeof(TileInfo64)));
     E_TRY(cudaMalloc(&e->d_errmax, sizeof(double)));
     E_TRY(cudaMallocHost(&e->h_errmax, sizeof(double)));
     E_TRY(cudaMemset(e->d_F, 0, 3 * n * rb));
@@ -442,7 +488,7 @@ extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax};
+    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (e->h_errmax) cudaFreeHost(e->h_errmax);
@@ -643,8 +689,9 @@ extern "C" int steps_b200_engine_sync(steps_b200_engine *e) {
 extern "C" int steps_b200_engine_launch_shape(steps_b200_engine *e, int id_min, int id_max, int *out4) {
     if (!e) return fail("engine is NULL");
     const bool tuned_f64 = (e->real_bytes == 8 && e->p.topology == STEPS_TOPO_R3);
-    const int ib = tuned_f64 ? F64_R * F64_THREADS : GEN_R * GEN_THREADS;
-    const int slots = e->num_sms * (tuned_f64 ? F64_MINB : 4);
+    const F64Variant fv = F64_VARIANTS[f64_variant()];
+    const int ib = tuned_f64 ? fv.R * fv.threads : GEN_R * GEN_THREADS;
+    const int slots = e->num_sms * (tuned_f64 ? fv.minb : 4);
     Plan pl = make_plan(id_max - id_min + 1, e->n, ib, slots, e->real_bytes);
     out4[0] = pl.ib_size;
     out4[1] = pl.n_chunks;

@@ -267,7 +267,7 @@ def test_dropin_forces_shim_inside_reference_build(name, variant):
         pytest.skip("oracle/_ref shim build not present")
     g, d = load_golden(name)
     r = pyref.Reference(variant, shim=True)
-    r.configure(g)
+    r.configure(g, 300)  # RADIAL_FORCE_ACCURACY the fixtures were generated with (tools/make_golden.py)
     r.build_tables()  # the reference's own builders fill its own globals; the shim packs them on every call
     F = r.forces(d["x"], 0, g.N - 1)
     e = rel_err(F, d["F"])
@@ -286,7 +286,7 @@ def test_dropin_step_shim_inside_reference_build(name, variant):
     g, d = load_golden(name)
     f64 = g.REAL == np.float64
     r = pyref.Reference(variant, shim=True)
-    r.configure(g)
+    r.configure(g, 300)
     r.build_tables()
     h0 = r.kdk_begin(d["x"], d["v"])
     assert math.isclose(h0, d["h_seq"][0], rel_tol=1e-11 if f64 else 1e-4)

@@ -2,6 +2,7 @@
 // chunk reduction + background term, and the device-resident KDK integrator (step.cc:100-312).
 #pragma once
 #include "pair_generic.cuh"
+#include "pair_r3_f32.cuh"
 
 namespace steps {
 
@@ -79,20 +80,64 @@ __global__ void __launch_bounds__(TJ_) pack_kernel_f64(const double *__restrict_
     }
 }
 
-__global__ void pack_kernel_f32(const float *__restrict__ x, const float *__restrict__ m, const float *__restrict__ s,
-                                const float *__restrict__ smax_tile, JRec32 *__restrict__ out, int n, int n_pad, int tj) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_pad) return;
+template <int TJ_>
+__global__ void __launch_bounds__(TJ_) pack_kernel_f32(const float *__restrict__ x, const float *__restrict__ m, const float *__restrict__ s,
+                                                        const float *__restrict__ smax_tile, JRec32 *__restrict__ out,
+                                                        TileInfo32 *__restrict__ tinfo, int n) {
+    const int t = blockIdx.x;
+    const int j = t * TJ_ + threadIdx.x;
     JRec32 r;
-    const float sm = smax_tile[j / tj];
+    const float sm = smax_tile[t];
+    float lo[3], hi[3], rlo, rhi;
     if (j < n) {
         r.x = x[3 * (size_t)j]; r.y = x[3 * (size_t)j + 1]; r.z = x[3 * (size_t)j + 2];
         r.m = m[j]; r.s = s[j]; r.smax = sm;
+        lo[0] = hi[0] = r.x; lo[1] = hi[1] = r.y; lo[2] = hi[2] = r.z;
+        // bounds must be conservative: round the radius down for rlo and up for rhi
+        const float r2 = r.x * r.x + r.y * r.y + r.z * r.z;
+        rlo = __fsqrt_rd(r2) * 0.999999f;
+        rhi = __fsqrt_ru(r2) * 1.000001f;
     } else {
         r.x = r.y = r.z = 1.0e15f; r.m = 0.f; r.s = 0.f; r.smax = sm;
+        lo[0] = lo[1] = lo[2] = rlo = 3.0e38f;
+        hi[0] = hi[1] = hi[2] = -3.0e38f;
+        rhi = 0.f;
     }
     r.p0 = r.p1 = 0.f;
     out[j] = r;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        rlo = fminf(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
+        rhi = fmaxf(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
+    }
+    __shared__ float red[TJ_ / 32][8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        red[w][0] = lo[0]; red[w][1] = lo[1]; red[w][2] = lo[2];
+        red[w][3] = hi[0]; red[w][4] = hi[1]; red[w][5] = hi[2];
+        red[w][6] = rlo; red[w][7] = rhi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        TileInfo32 ti;
+        ti.lo[0] = red[0][0]; ti.lo[1] = red[0][1]; ti.lo[2] = red[0][2];
+        ti.hi[0] = red[0][3]; ti.hi[1] = red[0][4]; ti.hi[2] = red[0][5];
+        ti.rlo = red[0][6]; ti.rhi = red[0][7];
+        for (int q = 1; q < TJ_ / 32; ++q) {
+            for (int k = 0; k < 3; ++k) {
+                ti.lo[k] = fminf(ti.lo[k], red[q][k]);
+                ti.hi[k] = fmaxf(ti.hi[k], red[q][3 + k]);
+            }
+            ti.rlo = fminf(ti.rlo, red[q][6]);
+            ti.rhi = fmaxf(ti.rhi, red[q][7]);
+        }
+        tinfo[t] = ti;
+    }
 }
 
 // linear interpolation of RADIAL_FORCE_TABLE, verbatim arithmetic of forces_cuda.cu:41-70

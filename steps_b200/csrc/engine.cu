@@ -125,11 +125,36 @@ int f64_variant() {
     }
     return v;
 }
+// tuned R^3 FP32 kernel shapes (STEPS_B200_F32_VARIANT=k for on-device tuning; 0 = production)
+struct F32Variant {
+    int R, threads, minb, unroll;
+};
+constexpr F32Variant F32_VARIANTS[] = {
+    {8, 256, 2, 2},   // 0: <=128 regs, 16 warps/SM
+    {16, 128, 2, 1},  // 1: <=255 regs, 8 warps/SM
+    {16, 128, 3, 1},  // 2: <=170 regs, 12 warps/SM
+    {8, 128, 4, 2},   // 3
+    {8, 128, 5, 2},   // 4: <=102 regs, 20 warps/SM
+    {12, 128, 3, 1},  // 5
+    {4, 256, 4, 4},   // 6: <=64 regs, 32 warps/SM
+    {8, 128, 4, 4},   // 7
+};
+constexpr int N_F32_VARIANTS = sizeof(F32_VARIANTS) / sizeof(F32_VARIANTS[0]);
+int f32_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("STEPS_B200_F32_VARIANT");
+        v = s ? atoi(s) : 0;
+        if (v < 0 || v >= N_F32_VARIANTS) v = 0;
+    }
+    return v;
+}
 // exact-branch kernels
 constexpr int GEN_R = 2, GEN_THREADS = 128, GEN_TJ = 128, GEN_STAGES = 3;
 constexpr int TJ = 128;  // j-tile (records) shared by all kernels so that one packed array serves all
 static_assert(F64_TJ == TJ && GEN_TJ == TJ, "one tile size");
 constexpr int MIN_TILES_PER_CHUNK = 8;
+constexpr int CTA_OVERHEAD_TILES = 2;
 
 struct Plan {
     int ib_size, n_ib, n_chunks, tiles_per_chunk, n_tiles, ctas, slots;
@@ -152,7 +177,9 @@ Plan make_plan(int n_i, int n, int ib_size, int slots, size_t real_bytes) {
         if ((size_t)ce * 3 * (size_t)n_i * real_bytes > mem_cap && c > 1) break;
         const long long units = (long long)p.n_ib * ce;
         const long long waves = (units + slots - 1) / slots;
-        const long long cost = waves * tpc;
+        // every CTA pays ~CTA_OVERHEAD_TILES tile-times of prologue/epilogue (i-load, pipeline fill, partial-sum
+        // store), every chunk one pass of the reduce kernel over the partial sums (~1/64 tile-time per i-block)
+        const long long cost = 64 * waves * (tpc + CTA_OVERHEAD_TILES) + (long long)ce * p.n_ib / slots;
         if (best < 0 || cost < best) {
             best = cost;
             p.n_chunks = ce;
@@ -278,14 +305,30 @@ int upload_tables(steps_b200_engine *e) {
     return 0;
 }
 
+Plan plan_for(const steps_b200_engine *e, int n_i) {
+    int ib = GEN_R * GEN_THREADS, per_sm = 4;
+    if (e->p.topology == STEPS_TOPO_R3) {
+        if (e->real_bytes == 8) {
+            const F64Variant fv = F64_VARIANTS[f64_variant()];
+            ib = fv.R * fv.threads;
+            per_sm = fv.minb;
+        } else {
+            const F32Variant gv = F32_VARIANTS[f32_variant()];
+            ib = gv.R * gv.threads;
+            per_sm = gv.minb;
+        }
+    }
+    return make_plan(n_i, e->n, ib, e->num_sms * per_sm, e->real_bytes);
+}
+
 template <typename T>
 int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     using JRec = typename JRecOf<T>::type;
     const bool tuned_f64 = (sizeof(T) == 8 && e->p.topology == STEPS_TOPO_R3);
+    const bool tuned_f32 = (sizeof(T) == 4 && e->p.topology == STEPS_TOPO_R3);
     const F64Variant fv = F64_VARIANTS[f64_variant()];
-    const int ib = tuned_f64 ? fv.R * fv.threads : GEN_R * GEN_THREADS;
-    const int slots = e->num_sms * (tuned_f64 ? fv.minb : 4);
-    Plan pl = make_plan(n_i, e->n, ib, slots, sizeof(T));
+    const F32Variant gv = F32_VARIANTS[f32_variant()];
+    Plan pl = plan_for(e, n_i);
     plan_out = pl;
     const size_t need = (size_t)pl.n_chunks * 3 * (size_t)n_i * sizeof(T);
     if (need > e->fpart_bytes) {
@@ -320,6 +363,20 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
             LAUNCH_F64(8) LAUNCH_F64(9) LAUNCH_F64(10) LAUNCH_F64(11) LAUNCH_F64(12) LAUNCH_F64(13) LAUNCH_F64(14) LAUNCH_F64(15)
         }
 #undef LAUNCH_F64
+    } else if (tuned_f32) {
+        const size_t smem = (size_t)F64_STAGES * (F64_TJ * sizeof(JRec32) + sizeof(TileInfo32)) + (size_t)(gv.threads / 32) * sizeof(WarpBounds32) +
+                            2 * F64_STAGES * sizeof(uint64_t);
+#define LAUNCH_F32(K)                                                                                                       \
+    case K: {                                                                                                               \
+        auto kern = force_r3_f32_kernel<F32_VARIANTS[K].R, F32_VARIANTS[K].threads, F64_TJ, F64_STAGES, F32_VARIANTS[K].minb, \
+                                        F32_VARIANTS[K].unroll>;                                                            \
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
+        kern<<<pl.ctas, F32_VARIANTS[K].threads, smem, e->stream>>>(a);                                                     \
+    } break;
+        switch (f32_variant()) {
+            LAUNCH_F32(0) LAUNCH_F32(1) LAUNCH_F32(2) LAUNCH_F32(3) LAUNCH_F32(4) LAUNCH_F32(5) LAUNCH_F32(6) LAUNCH_F32(7)
+        }
+#undef LAUNCH_F32
     } else {
         const size_t smem = (size_t)GEN_STAGES * GEN_TJ * sizeof(JRec) + 2 * GEN_STAGES * sizeof(uint64_t);
 #define LAUNCH_GEN(TOPO)                                                                                  \
@@ -348,13 +405,12 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
 }
 
 int pack(steps_b200_engine *e) {
-    const int blocks = (e->n_pad + 255) / 256;
     if (e->real_bytes == 8)
         pack_kernel_f64<TJ><<<e->n_tiles, TJ, 0, e->stream>>>((const double *)e->d_x, (const double *)e->d_m, (const double *)e->d_s,
                                                               (const double *)e->d_smax, (JRec64 *)e->d_jrec, (TileInfo64 *)e->d_tinfo, e->n);
     else
-        pack_kernel_f32<<<blocks, 256, 0, e->stream>>>((const float *)e->d_x, (const float *)e->d_m, (const float *)e->d_s,
-                                                       (const float *)e->d_smax, (JRec32 *)e->d_jrec, e->n, e->n_pad, TJ);
+        pack_kernel_f32<TJ><<<e->n_tiles, TJ, 0, e->stream>>>((const float *)e->d_x, (const float *)e->d_m, (const float *)e->d_s,
+                                                              (const float *)e->d_smax, (JRec32 *)e->d_jrec, (TileInfo32 *)e->d_tinfo, e->n);
     e->launches++;
     CU_TRY(cudaGetLastError());
     return 0;
@@ -467,7 +523,7 @@ extern "C" int steps_b200_engine_create(steps_b200_engine **out, const steps_b20
     E_TRY(cudaMalloc(&e->d_s, n * rb));
     E_TRY(cudaMalloc(&e->d_smax, (size_t)e->n_tiles * rb));
     E_TRY(cudaMalloc(&e->d_jrec, jrec_bytes));
-    E_TRY(cudaMalloc(&e->d_tinfo, (size_t)e->n_tiles * sizeof(TileInfo64)));
+    E_TRY(cudaMalloc(&e->d_tinfo, (size_t)e->n_tiles * sizeof(TileInfo64)));  // TileInfo32 is smaller
     E_TRY(cudaMalloc(&e->d_errmax, sizeof(double)));
     E_TRY(cudaMallocHost(&e->h_errmax, sizeof(double)));
     E_TRY(cudaMemset(e->d_F, 0, 3 * n * rb));
@@ -688,11 +744,7 @@ extern "C" int steps_b200_engine_sync(steps_b200_engine *e) {
 
 extern "C" int steps_b200_engine_launch_shape(steps_b200_engine *e, int id_min, int id_max, int *out4) {
     if (!e) return fail("engine is NULL");
-    const bool tuned_f64 = (e->real_bytes == 8 && e->p.topology == STEPS_TOPO_R3);
-    const F64Variant fv = F64_VARIANTS[f64_variant()];
-    const int ib = tuned_f64 ? fv.R * fv.threads : GEN_R * GEN_THREADS;
-    const int slots = e->num_sms * (tuned_f64 ? fv.minb : 4);
-    Plan pl = make_plan(id_max - id_min + 1, e->n, ib, slots, e->real_bytes);
+    Plan pl = plan_for(e, id_max - id_min + 1);
     out4[0] = pl.ib_size;
     out4[1] = pl.n_chunks;
     out4[2] = pl.ctas;

@@ -1,0 +1,97 @@
+"""GPU, >= 2 devices: the i-partitioned multi-GPU paths against the single-GPU result.
+  - steps_b200_forces_multi_*: the stateless call split over n_GPU devices (replaces forces_cuda(x,F,n_GPU,...))
+  - steps_b200_group_*: n resident engines in one process, NCCL position all-gather + errmax all-reduce per KDK step
+Skipped on a single-GPU box (the round-end GPU tier); run with `gpurun --gpus 2`."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import steps_b200 as sb
+from steps_b200 import _lib, ic
+
+pytestmark = pytest.mark.gpu
+
+
+def ndev():
+    return _lib.load().steps_b200_device_count()
+
+
+@pytest.fixture(autouse=True)
+def _need2():
+    if ndev() < 2:
+        pytest.skip("needs >= 2 GPUs")
+
+
+@pytest.mark.parametrize("n", [5000, 5001, 1023])
+def test_stateless_multi_gpu_split_matches_single(n):
+    c = ic.random_sphere(n, 7)
+    g = c.g
+    F1 = np.zeros(3 * n)
+    sb.forces(g, c.x, F1, 0, n - 1)
+    g.n_GPU = min(ndev(), 4)
+    F2 = np.full(3 * n, np.nan)
+    sb.forces(g, c.x, F2, 0, n - 1)
+    # different i-blocking and j-chunking per device: equal to rounding, not bitwise
+    scale = np.abs(F1).max()
+    assert np.abs(F1 - F2).max() / scale < 1e-13
+    lo, hi = 100, n - 37
+    F3 = np.full(3 * (hi - lo + 1), np.nan)
+    sb.forces(g, c.x, F3, lo, hi)
+    assert np.abs(F3 - F1[3 * lo: 3 * (hi + 1)]).max() / scale < 1e-13
+
+
+class Group:
+    def __init__(self, g, n_gpu):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        p = g.cparams()
+        _lib.check(self.lib.steps_b200_group_create(C.byref(self.h), C.byref(p), 8 if g.REAL == np.float64 else 4, n_gpu, 0))
+        self.g = g
+
+    def close(self):
+        self.lib.steps_b200_group_destroy(self.h)
+
+
+@pytest.mark.parametrize("REAL", [np.float64, np.float32])
+def test_group_kdk_matches_single_engine(REAL):
+    n = 6001
+    c = ic.random_sphere(n, 19, REAL)
+    g = c.g
+    # single engine
+    eng = sb.Engine(g, 0)
+    eng.upload(c.x, c.v)
+    eng.forces()
+    h = eng.calculate_init_h()
+    e1 = [eng.step(h) for _ in range(3)]
+    x1, v1, F1 = eng.download()
+    eng.close()
+    # group of 2..4 engines
+    k = min(ndev(), 4)
+    grp = Group(g, k)
+    lib = grp.lib
+    assert lib.steps_b200_group_size(grp.h) == k
+    _lib.check(lib.steps_b200_group_upload(grp.h, c.x.ctypes.data, c.v.ctypes.data, g.M.ctypes.data, g.SOFT_LENGTH.ctypes.data, None))
+    _lib.check(lib.steps_b200_group_forces(grp.h))
+    a0 = g.a_start
+    H0 = sb.CALCULATE_Hubble_param(g, a0)
+    em = C.c_double()
+    _lib.check(lib.steps_b200_group_init_errmax(grp.h, a0, H0, C.byref(em)))
+    h2 = (2 * g.ACC_PARAM / em.value) ** 0.5
+    tol = 1e-12 if REAL == np.float64 else 1e-4
+    assert abs(h2 - h) <= tol * h
+    a, H = a0, H0
+    e2 = []
+    for _ in range(3):
+        an = sb.friedmann_solver_step(g, a, h)
+        Hn = sb.CALCULATE_Hubble_param(g, an)
+        _lib.check(lib.steps_b200_group_kdk_step(grp.h, h, a, H, an, Hn, C.byref(em)))
+        a, H = an, Hn
+        e2.append(em.value)
+    x2, v2, F2 = (np.empty(3 * n, dtype=REAL) for _ in range(3))
+    _lib.check(lib.steps_b200_group_download(grp.h, x2.ctypes.data, v2.ctypes.data, F2.ctypes.data))
+    grp.close()
+    assert np.allclose(e1, e2, rtol=1e-10 if REAL == np.float64 else 1e-3)
+    assert np.abs(x1 - x2).max() / g.Rsim < (1e-13 if REAL == np.float64 else 1e-5)
+    assert np.abs(F1 - F2).max() / np.abs(F1).max() < (1e-12 if REAL == np.float64 else 1e-4)
+    assert np.abs(v1 - v2).max() / np.abs(v1).max() < (1e-12 if REAL == np.float64 else 1e-4)

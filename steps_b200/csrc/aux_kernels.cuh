@@ -278,11 +278,25 @@ __global__ void kick_errmax_kernel(T *__restrict__ x, T *__restrict__ v, const T
 
 // FMA-pipe microbenchmark: `iters` dependent-chain-free FMAs per thread on 8 accumulators
 template <typename T>
-__global__ void fma_peak_kernel(T *out, int iters, T a, T b) {
+__global__ void fma_peak_kernel(T *out, int iters, T a, T b, int pattern) {
+    if (pattern == 0) {  // c = fma(c, a, b): one varying register + two shared invariants (relies on the operand-reuse cache)
+        T c0 = threadIdx.x, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5, c6 = c0 + 6, c7 = c0 + 7;
+        for (int i = 0; i < iters; ++i) {
+            c0 = fma(c0, a, b); c1 = fma(c1, a, b); c2 = fma(c2, a, b); c3 = fma(c3, a, b);
+            c4 = fma(c4, a, b); c5 = fma(c5, a, b); c6 = fma(c6, a, b); c7 = fma(c7, a, b);
+        }
+        out[blockIdx.x * blockDim.x + threadIdx.x] = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
+        return;
+    }
+    // c_k = fma(y_k, y_k, c_k): two distinct source registers per FMA.  On sm_100 an FP64 instruction occupies the
+    // pipe for max(2, distinct non-reused 64-bit source registers) cycles per warp (tools/ubench2_fp64.cu), so this
+    // form issues at the pipe's real rate (2.04 cyc) where c = fma(c, a, b) with shared invariants measured 2.2-2.27.
     T c0 = threadIdx.x, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5, c6 = c0 + 6, c7 = c0 + 7;
+    const T t = (T)threadIdx.x * b;
+    const T y0 = a + t, y1 = a + 2 * t, y2 = a + 3 * t, y3 = a + 4 * t, y4 = a + 5 * t, y5 = a + 6 * t, y6 = a + 7 * t, y7 = a + 8 * t;
     for (int i = 0; i < iters; ++i) {
-        c0 = fma(c0, a, b); c1 = fma(c1, a, b); c2 = fma(c2, a, b); c3 = fma(c3, a, b);
-        c4 = fma(c4, a, b); c5 = fma(c5, a, b); c6 = fma(c6, a, b); c7 = fma(c7, a, b);
+        c0 = fma(y0, y0, c0); c1 = fma(y1, y1, c1); c2 = fma(y2, y2, c2); c3 = fma(y3, y3, c3);
+        c4 = fma(y4, y4, c4); c5 = fma(y5, y5, c5); c6 = fma(y6, y6, c6); c7 = fma(y7, y7, c7);
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
 }

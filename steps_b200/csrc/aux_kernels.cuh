@@ -3,6 +3,7 @@
 #pragma once
 #include "pair_generic.cuh"
 #include "pair_r3_f32.cuh"
+#include "pair_s1r2.cuh"
 
 namespace steps {
 
@@ -26,9 +27,14 @@ __global__ void tile_smax_kernel(const T *__restrict__ s, int n, int tj, int n_t
 template <int TJ_>
 __global__ void __launch_bounds__(TJ_) pack_kernel_f64(const double *__restrict__ x, const double *__restrict__ m, const double *__restrict__ s,
                                                         const double *__restrict__ smax_tile, JRec64 *__restrict__ out,
-                                                        TileInfo64 *__restrict__ tinfo, int n) {
+                                                        TileInfo64 *__restrict__ tinfo, int n, double zbox, int *__restrict__ z_outside, int planar) {
     const int t = blockIdx.x;
     const int j = t * TJ_ + threadIdx.x;
+    // S^1xR^2: note any z outside [0, L) (the tuned image-sum kernel assumes |dz| < L, pair_s1r2.cuh)
+    if (z_outside && j < n) {
+        const double zz = x[3 * (size_t)j + 2];
+        if (!(zz >= 0.0 && zz < zbox)) atomicOr(z_outside, 1);
+    }
     JRec64 r;
     const double sm = smax_tile[t];
     double lo[3], hi[3], rlo, rhi;
@@ -37,6 +43,10 @@ __global__ void __launch_bounds__(TJ_) pack_kernel_f64(const double *__restrict_
         r.m = m[j]; r.m15 = 1.5 * r.m; r.m1875 = 1.875 * r.m; r.s = s[j]; r.smax = sm;
         lo[0] = hi[0] = r.x; lo[1] = hi[1] = r.y; lo[2] = hi[2] = r.z;
         rlo = rhi = sqrt(r.x * r.x + r.y * r.y + r.z * r.z);
+        if (planar) {  // S^1xR^2: bounds in the x,y plane only (z is periodic), cylindrical radius
+            lo[2] = hi[2] = 0.0;
+            rlo = rhi = sqrt(r.x * r.x + r.y * r.y);
+        }
     } else {
         r.x = r.y = r.z = 1.0e20; r.m = r.m15 = r.m1875 = 0.0; r.s = 0.0; r.smax = sm;
         lo[0] = lo[1] = lo[2] = rlo = 1.0e300;

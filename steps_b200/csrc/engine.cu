@@ -118,6 +118,8 @@ constexpr F64Variant F64_VARIANTS[] = {
     {12, 128, 2, 1},    // 17
     {12, 64, 4, 1},     // 18
     {10, 64, 4, 1},     // 19
+    {8, 128, 1, 1},     // 20: ONE warp per SMSP (dynamic smem padded so that a single CTA fits per SM): no warp switching
+    {8, 128, 1, 2},     // 21: same, j unrolled by 2
 };
 constexpr int N_F64_VARIANTS = sizeof(F64_VARIANTS) / sizeof(F64_VARIANTS[0]);
 int f64_variant() {
@@ -207,6 +209,7 @@ struct steps_b200_engine {
     cudaStream_t stream = nullptr;
     void *d_x = nullptr, *d_v = nullptr, *d_F = nullptr, *d_m = nullptr, *d_s = nullptr;
     void *d_tinfo = nullptr;
+    int *d_zflag = nullptr;  // S^1xR^2: set by the pack kernel when some z lies outside [0, L)
     void *d_jrec = nullptr, *d_smax = nullptr, *d_fpart = nullptr, *d_table = nullptr, *d_radial = nullptr;
     double *d_errmax = nullptr, *h_errmax = nullptr;
     size_t fpart_bytes = 0;
@@ -309,8 +312,40 @@ int upload_tables(steps_b200_engine *e) {
     return 0;
 }
 
+// the tuned image-sum kernel of pair_s1r2.cuh: FP64 NOLOOKUP build with IS_PERIODIC in {2,3,4}
+struct S1R2Variant {
+    int R, threads, minb;
+};
+constexpr S1R2Variant S1R2_VARIANTS[] = {
+    {4, 128, 4},  // 0: PRODUCTION, 128 regs, 16 warps/SM
+    {2, 128, 8},  // 1: 64 regs, 32 warps/SM
+    {6, 128, 2},  // 2: 255 regs, 8 warps/SM
+    {3, 128, 5},  // 3: 102 regs, 20 warps/SM
+    {4, 256, 2},  // 4: 128 regs, 16 warps/SM in 256-thread CTAs
+    {8, 128, 2},  // 5: 255 regs
+};
+constexpr int N_S1R2_VARIANTS = sizeof(S1R2_VARIANTS) / sizeof(S1R2_VARIANTS[0]);
+int s1r2_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("STEPS_B200_S1R2_VARIANT");
+        v = s ? atoi(s) : 0;
+        if (v < 0 || v >= N_S1R2_VARIANTS) v = 0;
+    }
+    return v;
+}
+bool tuned_s1r2(const steps_b200_engine *e) {
+    static const bool off = getenv("STEPS_B200_NO_TUNED_S1R2") != nullptr;  // development switch: exact-branch kernel only
+    return !off && e->real_bytes == 8 && e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP && e->p.is_periodic >= 2 && e->p.is_periodic <= 4;
+}
+
 Plan plan_for(const steps_b200_engine *e, int n_i) {
     int ib = GEN_R * GEN_THREADS, per_sm = 4;
+    if (tuned_s1r2(e)) {
+        const S1R2Variant sv = S1R2_VARIANTS[s1r2_variant()];
+        ib = sv.R * sv.threads;
+        per_sm = sv.minb;
+    }
     if (e->p.topology == STEPS_TOPO_R3) {
         if (e->real_bytes == 8) {
             const F64Variant fv = F64_VARIANTS[f64_variant()];
@@ -353,8 +388,9 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     a.fstride = n_i;
     CU_TRY(cudaEventRecord(e->ev[4], e->stream));
     if (tuned_f64) {
-        const size_t smem = (size_t)F64_STAGES * (F64_TJ * sizeof(JRec64) + sizeof(TileInfo64)) + (size_t)(fv.threads / 32) * sizeof(WarpBounds64) +
-                            2 * F64_STAGES * sizeof(uint64_t);
+        size_t smem = (size_t)F64_STAGES * (F64_TJ * sizeof(JRec64) + sizeof(TileInfo64)) + (size_t)(fv.threads / 32) * sizeof(WarpBounds64) +
+                      2 * F64_STAGES * sizeof(uint64_t);
+        if (fv.minb == 1) smem = std::max(smem, (size_t)120 * 1024);  // occupancy limiter of the one-warp-per-SMSP shapes
 #define LAUNCH_F64(K)                                                                                                       \
     case K: {                                                                                                               \
         auto kern = force_r3_f64_kernel<F64_VARIANTS[K].R, F64_VARIANTS[K].threads, F64_TJ, F64_STAGES, F64_VARIANTS[K].minb, \
@@ -365,7 +401,7 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         switch (f64_variant()) {
             LAUNCH_F64(0) LAUNCH_F64(1) LAUNCH_F64(2) LAUNCH_F64(3) LAUNCH_F64(4) LAUNCH_F64(5) LAUNCH_F64(6) LAUNCH_F64(7)
             LAUNCH_F64(8) LAUNCH_F64(9) LAUNCH_F64(10) LAUNCH_F64(11) LAUNCH_F64(12) LAUNCH_F64(13) LAUNCH_F64(14) LAUNCH_F64(15)
-            LAUNCH_F64(16) LAUNCH_F64(17) LAUNCH_F64(18) LAUNCH_F64(19)
+            LAUNCH_F64(16) LAUNCH_F64(17) LAUNCH_F64(18) LAUNCH_F64(19) LAUNCH_F64(20) LAUNCH_F64(21)
         }
 #undef LAUNCH_F64
     } else if (tuned_f32) {
@@ -382,6 +418,44 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
             LAUNCH_F32(0) LAUNCH_F32(1) LAUNCH_F32(2) LAUNCH_F32(3) LAUNCH_F32(4) LAUNCH_F32(5) LAUNCH_F32(6) LAUNCH_F32(7)
         }
 #undef LAUNCH_F32
+    } else if (sizeof(T) == 8 && tuned_s1r2(e)) {
+        // tuned image-sum kernel when every z is inside [0, L) (device flag written by the pack kernel), else the exact-branch
+        // kernel in the same launch shape: both are launched, exactly one of them does the work
+        const S1R2Variant sv = S1R2_VARIANTS[s1r2_variant()];
+        const size_t smem = (size_t)GEN_STAGES * (GEN_TJ * sizeof(JRec64) + sizeof(TileInfo64)) + (size_t)(sv.threads / 32) * sizeof(WarpBounds64) +
+                            2 * GEN_STAGES * sizeof(uint64_t);
+        S1R2Consts k{};
+        k.L = e->tp.L;
+        k.cut = e->tp.ewald_cut * e->tp.L;
+        k.M = e->tp.ewald_max;
+        if (k.M < 3 || k.M > 5) return fail("tuned S^1xR^2 kernel: unsupported IS_PERIODIC");
+        // the tuned kernel runs when every z is inside [0, L) (device flag written by the pack kernel), else the exact-branch
+        // kernel in the same launch shape: both are launched, exactly one of them does the work
+#define LAUNCH_S1R2_VM(V, MM)                                                                                                        \
+    {                                                                                                                                \
+        a.gate = e->d_zflag;                                                                                                         \
+        a.gate_value = 0;                                                                                                            \
+        auto kern = force_s1r2nl_f64_kernel<S1R2_VARIANTS[V].R, S1R2_VARIANTS[V].threads, GEN_TJ, GEN_STAGES, S1R2_VARIANTS[V].minb, MM>; \
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                  \
+        kern<<<pl.ctas, S1R2_VARIANTS[V].threads, smem, e->stream>>>(a, k);                                                          \
+        e->launches++;                                                                                                               \
+        CU_TRY(cudaGetLastError());                                                                                                  \
+        a.gate_value = 1;                                                                                                            \
+        auto gen = force_generic_kernel<double, 3, S1R2_VARIANTS[V].R, S1R2_VARIANTS[V].threads, GEN_TJ, GEN_STAGES>;                \
+        CU_TRY(cudaFuncSetAttribute(gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                   \
+        gen<<<pl.ctas, S1R2_VARIANTS[V].threads, smem, e->stream>>>(a, e->tp);                                                       \
+    }
+#define LAUNCH_S1R2_V(V)                                                   \
+    case V:                                                                \
+        if (k.M == 3) LAUNCH_S1R2_VM(V, 3)                                 \
+        else if (k.M == 4) LAUNCH_S1R2_VM(V, 4)                            \
+        else LAUNCH_S1R2_VM(V, 5)                                          \
+        break;
+        switch (s1r2_variant()) {
+            LAUNCH_S1R2_V(0) LAUNCH_S1R2_V(1) LAUNCH_S1R2_V(2) LAUNCH_S1R2_V(3) LAUNCH_S1R2_V(4) LAUNCH_S1R2_V(5)
+        }
+#undef LAUNCH_S1R2_V
+#undef LAUNCH_S1R2_VM
     } else {
         const size_t smem = (size_t)GEN_STAGES * GEN_TJ * sizeof(JRec) + 2 * GEN_STAGES * sizeof(uint64_t);
 #define LAUNCH_GEN(TOPO)                                                                                  \
@@ -410,9 +484,16 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
 }
 
 int pack(steps_b200_engine *e) {
-    if (e->real_bytes == 8)
+    if (e->real_bytes == 8) {
+        int *zflag = nullptr;
+        if (tuned_s1r2(e)) {
+            zflag = e->d_zflag;
+            CU_TRY(cudaMemsetAsync(zflag, 0, sizeof(int), e->stream));
+        }
         pack_kernel_f64<TJ><<<e->n_tiles, TJ, 0, e->stream>>>((const double *)e->d_x, (const double *)e->d_m, (const double *)e->d_s,
-                                                              (const double *)e->d_smax, (JRec64 *)e->d_jrec, (TileInfo64 *)e->d_tinfo, e->n);
+                                                              (const double *)e->d_smax, (JRec64 *)e->d_jrec, (TileInfo64 *)e->d_tinfo, e->n,
+                                                              e->p.L, zflag, zflag != nullptr);
+    }
     else
         pack_kernel_f32<TJ><<<e->n_tiles, TJ, 0, e->stream>>>((const float *)e->d_x, (const float *)e->d_m, (const float *)e->d_s,
                                                               (const float *)e->d_smax, (JRec32 *)e->d_jrec, (TileInfo32 *)e->d_tinfo, e->n);
@@ -529,6 +610,8 @@ extern "C" int steps_b200_engine_create(steps_b200_engine **out, const steps_b20
     E_TRY(cudaMalloc(&e->d_smax, (size_t)e->n_tiles * rb));
     E_TRY(cudaMalloc(&e->d_jrec, jrec_bytes));
     E_TRY(cudaMalloc(&e->d_tinfo, (size_t)e->n_tiles * sizeof(TileInfo64)));  // TileInfo32 is smaller
+    E_TRY(cudaMalloc(&e->d_zflag, sizeof(int)));
+    E_TRY(cudaMemset(e->d_zflag, 0, sizeof(int)));
     E_TRY(cudaMalloc(&e->d_errmax, sizeof(double)));
     E_TRY(cudaMallocHost(&e->h_errmax, sizeof(double)));
     E_TRY(cudaMemset(e->d_F, 0, 3 * n * rb));
@@ -549,7 +632,7 @@ extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax};
+    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (e->h_errmax) cudaFreeHost(e->h_errmax);

@@ -251,6 +251,7 @@ __device__ __forceinline__ void pair_exact(const TopoParams &tp, T xi, T yi, T z
 
 template <typename T, int TOPO, int R, int THREADS, int TJ, int STAGES>
 __global__ void __launch_bounds__(THREADS) force_generic_kernel(const R3LaunchArgs a, const TopoParams tp) {
+    if (a.gate && *a.gate != a.gate_value) return;  // a tuned kernel handles this call (see pair_s1r2.cuh)
     using JRec = typename JRecOf<T>::type;
     constexpr int NWARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];

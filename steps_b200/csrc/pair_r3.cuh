@@ -89,6 +89,8 @@ struct R3LaunchArgs {
     int n_tiles;        // total j tiles
     int n_j;            // number of real j-particles (N)
     int fstride;        // >= n_i
+    const int *gate;    // optional device flag: the kernel returns at once unless *gate == gate_value (nullptr: always run)
+    int gate_value;
 };
 
 // Slow path of the tuned kernels: the pairs of one sub-block that the integer test flagged (r2 below the

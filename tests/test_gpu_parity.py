@@ -225,6 +225,55 @@ def test_periodic_topologies_vs_oracle_midsize(topo_case):
     assert e.max() < 50 * TOL64
 
 
+def _s1r2nl_reference_forces(c, radial_accuracy=400):
+    g = c.g
+    v = pyref.VARIANT[(g.topology, 8)]
+    if not pyref.available(v):
+        pytest.skip("tables need oracle/_ref")
+    r = pyref.Reference(v)
+    r.configure(g, radial_accuracy)
+    r.build_tables()
+    r.export_tables(g)
+    g.mass_in_unit_sphere = r.scalars()["mass_in_unit_sphere"]
+    return r.forces(c.x, 0, g.N - 1, 0)
+
+
+@pytest.mark.parametrize("is_periodic", [2, 3, 4])
+def test_s1r2nl_image_sum_kernel_all_image_counts(is_periodic):
+    """the tuned image-slot kernel (pair_s1r2.cuh) for M = IS_PERIODIC+1 = 3, 4, 5 against the reference's image loop,
+    including particles closer than a softening length and pairs whose +-(M-1), +-M images straddle the (M-0.4)L cut"""
+    c = ic.s1r2_cylinder(2500, 24, 60, 70 + is_periodic, lookup=False, is_periodic=is_periodic, L=20.0, r_sim=60.0, d_s=10.0, r_crit=15.0)
+    x = c.x.reshape(-1, 3)
+    x[1] = x[0] + [1e-3, -2e-3, 1.5e-3]          # deep inside the softening length
+    x[3] = x[2] + [0.0, 0.0, 0.4 * 20.0]         # dz exactly at the +-M selection threshold region
+    x[5] = x[4] + [0.01, 0.0, 0.6 * 20.0]        # dz at the +-(M-1) cut region
+    x[:, 2] = np.mod(x[:, 2], 20.0)
+    Fo = _s1r2nl_reference_forces(c)
+    F = gpu_forces(c.g, c.x, 0, c.g.N - 1)
+    e = rel_err(F, Fo)
+    print(f"s1r2nl IS_PERIODIC={is_periodic}: |dF|/|F| p99 {np.percentile(e, 99):.2e} max {e.max():.2e}")
+    assert np.percentile(e, 99) < TOL64
+    assert e.max() < 50 * TOL64
+
+
+def test_s1r2nl_z_outside_box_takes_exact_kernel():
+    """positions with z outside [0, L) (a caller that did not wrap): the engine must not use the |dz| < L shortcut"""
+    c = ic.s1r2_cylinder(2000, 24, 50, 77, lookup=False, is_periodic=2, L=20.0, r_sim=60.0, d_s=10.0, r_crit=15.0)
+    x = c.x.reshape(-1, 3)
+    x[::7, 2] += 20.0
+    x[3::11, 2] -= 40.0
+    Fo = _s1r2nl_reference_forces(c)
+    F = gpu_forces(c.g, c.x, 0, c.g.N - 1)
+    e = rel_err(F, Fo)
+    assert np.percentile(e, 99) < TOL64 and e.max() < 50 * TOL64
+    # and back inside the box on the same cached engine
+    x[:, 2] = np.mod(x[:, 2], 20.0)
+    Fo = _s1r2nl_reference_forces(c)
+    F = gpu_forces(c.g, c.x, 0, c.g.N - 1)
+    e = rel_err(F, Fo)
+    assert np.percentile(e, 99) < TOL64 and e.max() < 50 * TOL64
+
+
 def test_full_size_c2_properties():
     """BASELINE.json configs[1]: N = 2,000,000 FP64 compactified R^3 (size-independent properties + sampled oracle rows)"""
     c = ic.config_c2()

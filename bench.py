@@ -40,8 +40,11 @@ METRIC = "pair_interactions_per_s"
 UNIT = "pairs/s"
 
 
+_T0 = time.perf_counter()
+
+
 def log(*a):
-    print(*a, file=sys.stderr, flush=True)
+    print(f"[{time.perf_counter() - _T0:7.1f}s]", *a, file=sys.stderr, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ workload
@@ -223,8 +226,14 @@ def run_ours(args, out_fd):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: steps_b200 has no CPU path")
     torch.cuda.set_device(local)
+    os.environ["STEPS_B200_DEVICE"] = str(local)  # the stateless C-ABI calls (e2e leg) run on this rank's GPU
+    dev = f"cuda:{local}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+
+        log(f"[bench] rank {rank}/{world}: init_process_group(nccl) ...")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
+        log(f"[bench] rank {rank}: process group up")
 
     def barrier():
         if world > 1:
@@ -232,10 +241,10 @@ def run_ours(args, out_fd):
         torch.cuda.synchronize()
 
     def max_over_ranks(v: float) -> float:
-        return ranks.reduce_scalar(dist, world, v, "max", "cuda")
+        return ranks.reduce_scalar(dist, world, v, "max", dev)
 
     def sum_over_ranks(v: float) -> float:
-        return ranks.reduce_scalar(dist, world, v, "sum", "cuda")
+        return ranks.reduce_scalar(dist, world, v, "sum", dev)
 
     c = make_ic(args)  # same seeds on every rank -> bit-identical arrays
     g = c.g
@@ -244,10 +253,12 @@ def run_ours(args, out_fd):
     eng = sb.Engine(g, local)
     if world > 1:
         eng.comm_init(ranks.share_unique_id(dist, rank, world, sb.Engine.nccl_unique_id), rank, world)
+        log(f"[bench] rank {rank}: engine NCCL communicator up")
     eng.upload(c.x, c.v)
     eng.forces()
     h = eng.calculate_init_h()
     h = min(max(h, g.h_min), g.h_max)
+    log(f"[bench] rank {rank}: initial forces done, h0 = {h:.4e}")
 
     # FP pipe peak, measured live on this GPU (burst = kernel alone; sustained = 2 s back to back)
     peak_burst, implied_mhz = sb.fma_peak(local, rb)
@@ -325,6 +336,7 @@ def run_ours(args, out_fd):
         if rc != 0:
             raise SystemExit("e2e: " + lib.steps_b200_last_error().decode())
 
+    log(f"[bench] rank {rank}: timed steps done ({ms_step:.1f} ms/step), e2e leg ...")
     e2e_call()  # creates the cached engine of the stateless path
     barrier()
     t0 = time.perf_counter()
@@ -381,10 +393,21 @@ def main():
     sys.stdout.flush()
     out_fd = os.dup(1)
     os.dup2(2, 1)
-    if args.impl == "reference":
-        run_reference(args, out_fd)
-    else:
-        run_ours(args, out_fd)
+    try:
+        if args.impl == "reference":
+            run_reference(args, out_fd)
+        else:
+            run_ours(args, out_fd)
+    except BaseException as ex:  # noqa: BLE001
+        # under torchrun a rank that raises must die at once (no destructor may block on a collective), so that the
+        # launcher tears the other ranks down instead of letting them wait for the NCCL timeout
+        import traceback
+
+        traceback.print_exc()
+        sys.stderr.flush()
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not isinstance(ex, SystemExit):
+            os._exit(1)
+        raise
 
 
 if __name__ == "__main__":

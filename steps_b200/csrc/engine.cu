@@ -89,6 +89,21 @@ int nccl_load() {
     } while (0)
 }  // namespace
 
+// Every entry point that selects a device restores the caller's current device on return: a host program (PyTorch, an MPI
+// rank driving its own GPU) must not find its CUDA context switched by a library call.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ launch planning
 namespace {
 // tuned R^3 FP64 kernel shapes: {i-particles per thread, threads per CTA, resident CTAs per SM, j unroll}.
@@ -317,10 +332,10 @@ struct S1R2Variant {
     int R, threads, minb;
 };
 constexpr S1R2Variant S1R2_VARIANTS[] = {
-    {4, 128, 4},  // 0: PRODUCTION, 128 regs, 16 warps/SM
+    {4, 128, 4},  // 0: 128 regs, 16 warps/SM
     {2, 128, 8},  // 1: 64 regs, 32 warps/SM
     {6, 128, 2},  // 2: 255 regs, 8 warps/SM
-    {3, 128, 5},  // 3: 102 regs, 20 warps/SM
+    {3, 128, 5},  // 3: PRODUCTION.  102 regs, 20 warps/SM
     {4, 256, 2},  // 4: 128 regs, 16 warps/SM in 256-thread CTAs
     {8, 128, 2},  // 5: 255 regs
 };
@@ -329,8 +344,8 @@ int s1r2_variant() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("STEPS_B200_S1R2_VARIANT");
-        v = s ? atoi(s) : 0;
-        if (v < 0 || v >= N_S1R2_VARIANTS) v = 0;
+        v = s ? atoi(s) : 3;  // production shape: fastest of the sweep in profiles/ (R=3, 20 warps/SM)
+        if (v < 0 || v >= N_S1R2_VARIANTS) v = 3;
     }
     return v;
 }
@@ -505,6 +520,7 @@ int pack(steps_b200_engine *e) {
 int forces_impl(steps_b200_engine *e, int id_min, int id_max) {
     if (!e->have_state) return fail("engine has no particle state: call upload first");
     if (id_min < 0 || id_max >= e->n || id_max < id_min) return fail("bad [id_min, id_max]");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     CU_TRY(cudaEventRecord(e->ev[0], e->stream));
     if (pack(e)) return 1;
@@ -577,6 +593,7 @@ extern "C" int steps_b200_engine_create(steps_b200_engine **out, const steps_b20
         return fail("no CUDA device available: libstepsb200 has no CPU fallback");
     }
     if (device < 0 || device >= ndev) return fail("bad device ordinal");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
@@ -629,6 +646,7 @@ extern "C" int steps_b200_engine_create(steps_b200_engine **out, const steps_b20
 
 extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
     if (!e) return;
+    DeviceGuard dg_;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
@@ -661,6 +679,7 @@ extern "C" int steps_b200_engine_comm_init(steps_b200_engine *e, const void *id1
     steps_b200_partition(e->n, nranks, rank, &e->i_lo, &e->i_hi);
     if (nranks == 1) return 0;
     if (nccl_load()) return 1;
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     ncclUniqueId id;
     memcpy(&id, id128, 128);
@@ -671,6 +690,7 @@ extern "C" int steps_b200_engine_comm_init(steps_b200_engine *e, const void *id1
 extern "C" int steps_b200_engine_upload(steps_b200_engine *e, const void *x, const void *v, const void *M, const void *soft) {
     if (!e) return fail("engine is NULL");
     if (!x || !M || !soft) return fail("x, M, soft must be non-NULL");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     const size_t rb = e->real_bytes, n = e->n;
     CU_TRY(cudaMemcpyAsync(e->d_x, x, 3 * n * rb, cudaMemcpyHostToDevice, e->stream));
@@ -691,6 +711,7 @@ extern "C" int steps_b200_engine_upload(steps_b200_engine *e, const void *x, con
 extern "C" int steps_b200_engine_upload_x(steps_b200_engine *e, const void *x) {
     if (!e) return fail("engine is NULL");
     if (!e->have_state) return fail("upload_x before upload");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     CU_TRY(cudaMemcpyAsync(e->d_x, x, 3 * (size_t)e->n * e->real_bytes, cudaMemcpyHostToDevice, e->stream));
     return 0;
@@ -699,6 +720,7 @@ extern "C" int steps_b200_engine_upload_x(steps_b200_engine *e, const void *x) {
 extern "C" int steps_b200_engine_upload_forces(steps_b200_engine *e, const void *F) {
     if (!e) return fail("engine is NULL");
     if (!F) return fail("F is NULL");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     CU_TRY(cudaMemcpyAsync(e->d_F, F, 3 * (size_t)e->n * e->real_bytes, cudaMemcpyHostToDevice, e->stream));
     return 0;
@@ -712,6 +734,7 @@ extern "C" int steps_b200_engine_forces(steps_b200_engine *e, int id_min, int id
 extern "C" int steps_b200_engine_download_forces(steps_b200_engine *e, void *F, int id_min, int id_max) {
     if (!e) return fail("engine is NULL");
     if (id_min < 0 || id_max >= e->n || id_max < id_min) return fail("bad [id_min, id_max]");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     const size_t rb = e->real_bytes;
     CU_TRY(cudaMemcpyAsync(F, static_cast<char *>(e->d_F) + 3 * (size_t)id_min * rb, 3 * (size_t)(id_max - id_min + 1) * rb,
@@ -722,6 +745,7 @@ extern "C" int steps_b200_engine_download_forces(steps_b200_engine *e, void *F, 
 
 extern "C" int steps_b200_engine_download(steps_b200_engine *e, void *x, void *v, void *F) {
     if (!e) return fail("engine is NULL");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     const size_t bytes = 3 * (size_t)e->n * e->real_bytes;
     if (x) CU_TRY(cudaMemcpyAsync(x, e->d_x, bytes, cudaMemcpyDeviceToHost, e->stream));
@@ -745,6 +769,7 @@ static int errmax_launch(steps_b200_engine *e, const KdkScalars &k, int do_kick,
 extern "C" int steps_b200_engine_init_errmax(steps_b200_engine *e, double a, double hubble, double *errmax_out) {
     if (!e) return fail("engine is NULL");
     if (!e->have_state) return fail("engine has no particle state");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     const KdkScalars k = kdk_scalars(e, 0.0, a, hubble);
     int rc = e->real_bytes == 8 ? errmax_launch<double>(e, k, 0, 1) : errmax_launch<float>(e, k, 0, 1);
@@ -756,6 +781,7 @@ extern "C" int steps_b200_engine_kdk_step(steps_b200_engine *e, double h, double
                                           double hubble_new, double *errmax_out) {
     if (!e) return fail("engine is NULL");
     if (!e->have_state) return fail("engine has no particle state");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     CU_TRY(cudaEventRecord(e->ev[2], e->stream));
     const int cnt = e->i_hi - e->i_lo;
@@ -778,6 +804,7 @@ extern "C" int steps_b200_engine_kdk_step(steps_b200_engine *e, double h, double
 
 extern "C" int steps_b200_engine_timings(steps_b200_engine *e, double *force_ms, double *step_ms) {
     if (!e) return fail("engine is NULL");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     CU_TRY(cudaStreamSynchronize(e->stream));
     float f = 0.f, s = 0.f;
@@ -794,6 +821,7 @@ extern "C" int steps_b200_engine_timings(steps_b200_engine *e, double *force_ms,
 
 extern "C" int steps_b200_engine_pair_kernel_ms(steps_b200_engine *e, double *ms_out) {
     if (!e || !ms_out) return fail("engine or output is NULL");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     CU_TRY(cudaStreamSynchronize(e->stream));
     float f = 0.f;
@@ -805,6 +833,7 @@ extern "C" int steps_b200_engine_pair_kernel_ms(steps_b200_engine *e, double *ms
 extern "C" int steps_b200_engine_mark(steps_b200_engine *e, int slot) {
     if (!e) return fail("engine is NULL");
     if (slot < 0 || slot >= 8) return fail("mark slot must be 0..7");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     CU_TRY(cudaEventRecord(e->marks[slot], e->stream));
     return 0;
@@ -813,6 +842,7 @@ extern "C" int steps_b200_engine_mark(steps_b200_engine *e, int slot) {
 extern "C" int steps_b200_engine_elapsed_ms(steps_b200_engine *e, int slot_a, int slot_b, double *ms_out) {
     if (!e || !ms_out) return fail("engine or output is NULL");
     if (slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8) return fail("mark slot must be 0..7");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     CU_TRY(cudaEventSynchronize(e->marks[slot_b]));
     float f = 0.f;
@@ -825,6 +855,7 @@ extern "C" long long steps_b200_engine_launch_count(steps_b200_engine *e) { retu
 
 extern "C" int steps_b200_engine_sync(steps_b200_engine *e) {
     if (!e) return fail("engine is NULL");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     CU_TRY(cudaStreamSynchronize(e->stream));
     return 0;
@@ -872,7 +903,9 @@ int forces_stateless(const steps_b200_params *p, int real_bytes, const void *x, 
     if (n_gpu > n_i) n_gpu = n_i;
     const int pi = real_bytes == 8 ? 0 : 1;
     int lo[MAX_DEV], hi[MAX_DEV];
+    DeviceGuard dg_;  // the caller's current device is restored on every return path
     for (int d = 0; d < n_gpu; ++d) {
+        CU_TRY(cudaSetDevice(first_device + d));
         steps_b200_partition(n_i, n_gpu, d, &lo[d], &hi[d]);
         lo[d] += id_min;
         hi[d] += id_min;  // exclusive
@@ -1059,6 +1092,7 @@ extern "C" int steps_b200_group_download(steps_b200_group *g, void *x, void *v, 
     const size_t rb = g->real_bytes;
     for (size_t d = 0; d < g->eng.size(); ++d) {
         steps_b200_engine *e = g->eng[d];
+        DeviceGuard dg_;
         CU_TRY(cudaSetDevice(e->device));
         if (x && d == 0) CU_TRY(cudaMemcpyAsync(x, e->d_x, 3 * (size_t)e->n * rb, cudaMemcpyDeviceToHost, e->stream));
         const size_t off = 3 * (size_t)e->i_lo * rb, len = 3 * (size_t)(e->i_hi - e->i_lo) * rb;
@@ -1153,6 +1187,7 @@ extern "C" int steps_b200_fma_peak(int device, int real_bytes, double *tflops_ou
         cudaGetLastError();
         return fail("no CUDA device available");
     }
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
@@ -1197,6 +1232,7 @@ extern "C" int steps_b200_fma_peak_sustained(int device, int real_bytes, double 
         return fail("no CUDA device available");
     }
     if (!tflops_out || !(seconds > 0.0)) return fail("bad arguments");
+    DeviceGuard dg_;
     CU_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));

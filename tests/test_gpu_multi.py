@@ -95,3 +95,26 @@ def test_group_kdk_matches_single_engine(REAL):
     assert np.abs(x1 - x2).max() / g.Rsim < (1e-13 if REAL == np.float64 else 1e-5)
     assert np.abs(F1 - F2).max() / np.abs(F1).max() < (1e-12 if REAL == np.float64 else 1e-4)
     assert np.abs(v1 - v2).max() / np.abs(v1).max() < (1e-12 if REAL == np.float64 else 1e-4)
+
+
+def test_library_calls_restore_the_callers_current_device():
+    """a host program's current CUDA device must survive every library call (bench.py's ranks, MPI ranks with their own GPU)"""
+    import torch
+
+    torch.cuda.set_device(1)
+    try:
+        c = ic.random_sphere(2000, 3)
+        F = np.zeros(3 * 2000)
+        sb.forces(c.g, c.x, F, 0, 1999)  # stateless call, runs on $STEPS_B200_DEVICE (default 0)
+        assert torch.cuda.current_device() == 1
+        eng = sb.Engine(c.g, 0)
+        eng.upload(c.x, c.v)
+        eng.forces()
+        eng.sync()
+        assert torch.cuda.current_device() == 1
+        t = torch.zeros(4, device="cuda")
+        assert t.device.index == 1
+        eng.close()
+        assert torch.cuda.current_device() == 1
+    finally:
+        torch.cuda.set_device(0)

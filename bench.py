@@ -16,7 +16,9 @@ What the keys mean here (see DESIGN.md "Measurement"):
   e2e       the same metric through the reference-facing C-ABI call steps_b200_forces_f64() with HOST
             (pinned) buffers: H2D of x, M, s and D2H of F are inside the timed region, every step.
   roofline  the pair kernel against the FP64 FMA pipe (this path is FP64-pipe bound, not HBM or tensor):
-            achieved = 20 flop x pair evaluations per launch / CUDA-event duration of that launch,
+            achieved = 20 flop x pair INTERACTIONS per launch (the reference's count, n_i x N) / CUDA-event duration of
+            the pair phase (the action-reaction path delivers two interactions per evaluation, so its achieved
+            figure can exceed what 15 instructions per directed pair allow),
             peak = DFMA microbenchmark measured live on the same GPU (MEASURED_PEAKS.json has no FP64 entry).
   cpu_baseline  oracle/_ref (the unmodified reference, kind "reference") or the plain-C port (kind "port")
             on a bounded i-subrange of the same workload, all host threads.
@@ -69,9 +71,12 @@ def make_ic(args):
     return c
 
 
-def workload_config(c, world):
+def workload_config(c, world, symmetric=False):
     g = c.g
     return {
+        "evaluation": ("action-reaction: every unordered pair evaluated once and applied to both particles (N(N+1)/2 evaluations "
+                       "deliver the N^2 interactions the reference evaluates one by one)") if symmetric else
+                      "one-sided: N^2 directed pair evaluations, as the reference",
         "workload": f"{c.name}: one KDK step (kick+drift, position all-gather, N^2 direct-sum force, kick+errmax), "
                     "mass-dependent pairwise softening, comoving LCDM background term",
         "baseline_config": "configs[1]" if "C2" in c.name else c.name.split()[0],
@@ -306,9 +311,11 @@ def run_ours(args, out_fd):
             traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             traffic = None
+    symmetric = eng.symmetric
     roofline = {
         "bound": "fp64_pipe" if rb == 8 else "fp32_pipe",
-        "kernel": "force_r3_f64_kernel" if rb == 8 else "force_generic_kernel<float>",
+        "kernel": ("force_r3_f64_sym_kernel" if symmetric else "force_r3_f64_kernel") if rb == 8 else "force_r3_f32_kernel",
+        "fp64_instr_per_interaction": (10 if symmetric else 15) if rb == 8 else None,
         "achieved": achieved_tf, "peak": peak_sust, "unit": "TFLOP/s", "frac": achieved_tf / peak_sust,
         "peak_burst": peak_burst, "frac_of_burst": achieved_tf / peak_burst,
         "peak_source": "DFMA/FFMA microbenchmark (steps_b200_fma_peak_sustained: 2 s back to back; burst = best single launch) "
@@ -351,7 +358,7 @@ def run_ours(args, out_fd):
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(float(h2d))),
            "d2h_bytes_per_step": int(sum_over_ranks(float(d2h))), "ms_per_step": 1e3 * t_e2e / args.steps,
            "call": "steps_b200_forces_f64(params, x, M, soft, F, id_min, id_max) with pinned host buffers; wall clock around K synchronous calls, max over ranks"}
-    launches_e2e = 4 * args.steps  # pack + pair + reduce + tile_smax per call
+    launches_e2e = 4 * args.steps  # pack + pair + reduce + tile_smax per call (lower bound: the action-reaction path adds one row reduction per pass)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -364,7 +371,7 @@ def run_ours(args, out_fd):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "s_per_step": ms_step * 1e-3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64" if rb == 8 else "f32", "data": "synthetic", "config": workload_config(c, world),
+            "vs_baseline": None, "dtype": "f64" if rb == 8 else "f32", "data": "synthetic", "config": workload_config(c, world, symmetric),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "gpu_launches_e2e": launches_e2e,
             "clocks": clocks, "tflops_20flop": FLOP_PER_PAIR * value / 1e12,
             "frac_of_fp_peak_whole_job": FLOP_PER_PAIR * value / 1e12 / (peak_sust * world),

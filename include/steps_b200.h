@@ -110,6 +110,21 @@ void steps_b200_engine_destroy(steps_b200_engine *e);
  * and forces_cuda.cu:942-951, which give the whole remainder to rank/GPU 0). */
 void steps_b200_partition(int n, int nranks, int rank, int *i_lo, int *i_hi);
 
+/* Action-reaction evaluation of the R^3 FP64 path (pair_r3_sym.cuh): every unordered pair is evaluated once and
+ * applied to both particles (F_i += m_j w d, F_j -= m_i w d), the same force law as forces() (forces.cc:510-577).
+ * It serves force calls for exactly the engine's own rows; multi-GPU engines then partition rows on i-block
+ * boundaries and exchange the j-side sums with one all-reduce per evaluation.  Default: environment variable
+ * STEPS_B200_SYM (0/1).  set_symmetric() must precede comm_init() and is collective in spirit: every rank of a job
+ * must make the same choice.  engine_range() returns the rows [i_lo, i_hi) the engine owns under the partition
+ * in force.  sym_rules() is the host-only rule builder (no GPU needed): for rank `rank` of `nranks`, i-block size
+ * ib_size (a multiple of the 128-record j-tile), it writes 16 ints per local i-block
+ * {diag_lo, diag_hi, n_sym, sym_lo[5], sym_hi[5], pad[3]} (tile indices) and returns the number of blocks, or -1
+ * when the geometry does not admit the symmetric path. */
+int steps_b200_engine_set_symmetric(steps_b200_engine *e, int on);
+int steps_b200_engine_is_symmetric(steps_b200_engine *e);
+int steps_b200_engine_range(steps_b200_engine *e, int *i_lo, int *i_hi);
+int steps_b200_sym_rules(int n, int nranks, int rank, int ib_size, int *i_lo, int *i_hi, int *rules_out, int max_blocks);
+
 /* NCCL bootstrap for one-process-per-GPU runs: rank 0 calls unique_id() and ships the 128 bytes to
  * the others by any means (MPI_Bcast in StePS, torch.distributed in bench.py); then every rank
  * calls comm_init().  Without comm_init the engine is single-GPU and owns [0, n). */

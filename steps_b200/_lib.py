@@ -69,6 +69,10 @@ SYMBOLS = {
     "steps_b200_engine_create": (_I, [C.POINTER(_VP), _PP, _I, _I]),
     "steps_b200_engine_destroy": (None, [_VP]),
     "steps_b200_partition": (None, [_I, _I, _I, _PI, _PI]),
+    "steps_b200_engine_set_symmetric": (_I, [_VP, _I]),
+    "steps_b200_engine_is_symmetric": (_I, [_VP]),
+    "steps_b200_engine_range": (_I, [_VP, _PI, _PI]),
+    "steps_b200_sym_rules": (_I, [_I, _I, _I, _I, _PI, _PI, _PI, _I]),
     "steps_b200_nccl_unique_id": (_I, [_VP]),
     "steps_b200_engine_comm_init": (_I, [_VP, _VP, _I, _I]),
     "steps_b200_engine_upload": (_I, [_VP, _VP, _VP, _VP, _VP]),

@@ -209,6 +209,17 @@ def partition(n: int, nranks: int, rank: int) -> tuple:
     return lo.value, hi.value
 
 
+def sym_rules(n: int, nranks: int, rank: int, ib_size: int):
+    """host-only rule builder of the action-reaction path: -> (i_lo, i_hi, rules[nb, 16]) or None"""
+    nb_max = (n + ib_size - 1) // ib_size + 1
+    out = np.zeros((nb_max, 16), dtype=np.int32)
+    lo, hi = C.c_int(), C.c_int()
+    nb = _lib.load().steps_b200_sym_rules(n, nranks, rank, ib_size, C.byref(lo), C.byref(hi), out.ctypes.data_as(C.POINTER(C.c_int)), nb_max)
+    if nb < 0:
+        return None
+    return lo.value, hi.value, out[:nb]
+
+
 def fma_peak(device: int, real_bytes: int) -> tuple:
     """measured FMA-pipe TFLOP/s (2 flop/FMA) and implied SM clock (MHz) -- the roofline denominator"""
     tf, mhz = C.c_double(), C.c_double()
@@ -262,7 +273,22 @@ class Engine:
     def comm_init(self, unique_id: bytes, rank: int, nranks: int) -> None:
         buf = C.create_string_buffer(unique_id, 128)
         check(self.lib.steps_b200_engine_comm_init(self._h, buf, rank, nranks))
-        self.i_lo, self.i_hi = partition(self.g.N, nranks, rank)
+        self.i_lo, self.i_hi = self.range()
+
+    def range(self) -> tuple:
+        """rows [i_lo, i_hi) this engine owns under the partition in force (i-block aligned in symmetric mode)"""
+        lo, hi = C.c_int(), C.c_int()
+        check(self.lib.steps_b200_engine_range(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def set_symmetric(self, on: bool) -> None:
+        """action-reaction evaluation of the R^3 FP64 path (before comm_init; every rank the same choice)"""
+        check(self.lib.steps_b200_engine_set_symmetric(self._h, 1 if on else 0))
+        self.i_lo, self.i_hi = self.range()
+
+    @property
+    def symmetric(self) -> bool:
+        return bool(self.lib.steps_b200_engine_is_symmetric(self._h))
 
     def upload(self, x: np.ndarray, v: Optional[np.ndarray] = None) -> None:
         g = self.g

@@ -4,6 +4,7 @@
 #include "pair_generic.cuh"
 #include "pair_r3_f32.cuh"
 #include "pair_s1r2.cuh"
+#include "pair_r3_sym.cuh"
 
 namespace steps {
 
@@ -166,10 +167,13 @@ __device__ __forceinline__ T cylindrical_force_correction(T r, T R, const T *__r
 }
 
 // F_i = sum over j-chunks (fixed order c = 0..n_chunks-1: deterministic) + background term.
-// Writes AoS F at GLOBAL particle index (id_min + il).
+// Writes AoS F at GLOBAL particle index (id_min + il).  fsym (optional): the j-side sums of the action-reaction
+// kernel (pair_r3_sym.cuh), SoA [3][fsym_stride] by global particle index, accumulated with the sign of d = x_j - x_i
+// as seen from the OTHER particle, hence subtracted here.
 template <typename T>
 __global__ void reduce_kernel(const T *__restrict__ fpart, int n_chunks, int fstride, int n_i, int id_min,
-                              const T *__restrict__ x, T *__restrict__ F, const TopoParams tp) {
+                              const T *__restrict__ x, T *__restrict__ F, const TopoParams tp, const T *__restrict__ fsym,
+                              size_t fsym_stride) {
     const int il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il >= n_i) return;
     T fx = 0, fy = 0, fz = 0;
@@ -180,6 +184,11 @@ __global__ void reduce_kernel(const T *__restrict__ fpart, int n_chunks, int fst
         fz += p[2 * (size_t)fstride + il];
     }
     const size_t i = (size_t)id_min + il;
+    if (fsym) {
+        fx -= fsym[i];
+        fy -= fsym[fsym_stride + i];
+        fz -= fsym[2 * fsym_stride + i];
+    }
     const T xi = x[3 * i], yi = x[3 * i + 1], zi = x[3 * i + 2];
     if (tp.bg_mode != 0) {
         const T B = (T)tp.bg_coeff;

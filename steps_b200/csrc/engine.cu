@@ -4,6 +4,7 @@
 //
 // There is NO CPU fallback in this file: every compute entry point needs a CUDA device and
 // fails with an error message otherwise.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -234,6 +235,13 @@ struct steps_b200_engine {
     long long launches = 0;
     bool have_state = false;
     TopoParams tp{};
+    // action-reaction (symmetric) R^3 FP64 path, pair_r3_sym.cuh
+    bool sym = false;            // requested (STEPS_B200_SYM / steps_b200_engine_set_symmetric) and applicable
+    int sym_ib = 0;              // i-block size of the symmetric kernel shape
+    std::vector<SymRule> h_rules;  // one per local i-block of [i_lo, i_hi)
+    SymRule *d_rules = nullptr;
+    double *d_gpart = nullptr, *d_fsym = nullptr;
+    size_t gpart_bytes = 0;
 };
 
 namespace {
@@ -352,6 +360,162 @@ int s1r2_variant() {
 bool tuned_s1r2(const steps_b200_engine *e) {
     static const bool off = getenv("STEPS_B200_NO_TUNED_S1R2") != nullptr;  // development switch: exact-branch kernel only
     return !off && e->real_bytes == 8 && e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP && e->p.is_periodic >= 2 && e->p.is_periodic <= 4;
+}
+
+
+// ---------------------------------------------------------------- action-reaction path (pair_r3_sym.cuh)
+struct SymVariant {
+    int R, threads, minb;
+};
+constexpr SymVariant SYM_VARIANTS[] = {
+    {6, 128, 2},  // 0: 253 registers, no spills; i-block 768
+    {8, 128, 2},  // 1: 255 registers, a few spills outside the hot loop; i-block 1024
+    {7, 128, 2},  // 2: i-block 896
+};
+constexpr int N_SYM_VARIANTS = sizeof(SYM_VARIANTS) / sizeof(SYM_VARIANTS[0]);
+int sym_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("STEPS_B200_SYM_VARIANT");
+        v = s ? atoi(s) : 0;
+        if (v < 0 || v >= N_SYM_VARIANTS) v = 0;
+    }
+    return v;
+}
+bool sym_env_default() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("STEPS_B200_SYM");
+        v = (s && atoi(s) != 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+constexpr int SYM_TARGET_CHUNKS = 56;
+
+// i-blocks [blo, bhi) of rank r when nb_total blocks are dealt out contiguously, remainder one-each to the first ranks
+void sym_block_range(int nb_total, int nranks, int r, int &blo, int &bhi) {
+    const int base = nb_total / nranks, rem = nb_total % nranks;
+    blo = r * base + (r < rem ? r : rem);
+    bhi = blo + base + (r < rem ? 1 : 0);
+}
+
+// The rules of rank `rank`: which j-tiles each of its i-blocks evaluates one-sidedly (its own particles), which
+// symmetrically (once for both sides), and which it leaves to the CTA of the other block.  Every unordered pair of
+// blocks (A, B) of the whole job is assigned to exactly one side:
+//   same rank:                the lower block A takes B's tiles;
+//   ranks p != q, k = (q - p) mod P:   1 <= k <= (P-1)/2  -> p's blocks take all tiles of q (ring assignment);
+//   P even, k = P/2 (p < q):  p's blocks take the tiles of the FIRST half of q's blocks, and the SECOND half of q's
+//                             blocks take all tiles of p.
+// Returns 0, or 1 when the geometry does not allow the symmetric path (caller falls back to the one-sided kernel).
+int build_sym_rules(int n, int nranks, int rank, int ib_size, int tj, std::vector<SymRule> &out, int *i_lo, int *i_hi) {
+    out.clear();
+    if (ib_size % tj != 0) return 1;
+    const int tpb = ib_size / tj;
+    const int n_tiles = (n + tj - 1) / tj;
+    const int nb_total = (n + ib_size - 1) / ib_size;
+    if (nb_total < 2 * nranks) return 1;
+    auto tlo = [&](int q) { int a, b; sym_block_range(nb_total, nranks, q, a, b); return std::min(a * tpb, n_tiles); };
+    auto thi = [&](int q) { int a, b; sym_block_range(nb_total, nranks, q, a, b); return std::min(b * tpb, n_tiles); };
+    int blo, bhi;
+    sym_block_range(nb_total, nranks, rank, blo, bhi);
+    if (i_lo) *i_lo = std::min(blo * ib_size, n);
+    if (i_hi) *i_hi = std::min(bhi * ib_size, n);
+    const int nbp = bhi - blo;
+    const int half = nranks / 2;
+    for (int b = 0; b < nbp; ++b) {
+        const int gb = blo + b;
+        std::vector<std::pair<int, int>> rg;
+        auto add = [&](int lo, int hi) { if (lo < hi) rg.emplace_back(lo, hi); };
+        add(std::min((gb + 1) * tpb, n_tiles), thi(rank));
+        for (int k = 1; k <= (nranks - 1) / 2; ++k) {
+            const int q = (rank + k) % nranks;
+            add(tlo(q), thi(q));
+        }
+        if (nranks % 2 == 0 && nranks > 1) {
+            if (rank < half) {
+                const int q = rank + half;
+                int qa, qb;
+                sym_block_range(nb_total, nranks, q, qa, qb);
+                add(tlo(q), std::min((qa + (qb - qa) / 2) * tpb, n_tiles));
+            } else if (b >= nbp / 2) {
+                const int q = rank - half;
+                add(tlo(q), thi(q));
+            }
+        }
+        std::sort(rg.begin(), rg.end());
+        std::vector<std::pair<int, int>> mg;
+        for (auto &r : rg) {
+            if (!mg.empty() && r.first <= mg.back().second) mg.back().second = std::max(mg.back().second, r.second);
+            else mg.push_back(r);
+        }
+        if ((int)mg.size() > SYM_MAX_RANGES) return 1;
+        SymRule ru{};
+        ru.diag_lo = std::min(gb * tpb, n_tiles);
+        ru.diag_hi = std::min((gb + 1) * tpb, n_tiles);
+        ru.n_sym = (int)mg.size();
+        for (int k = 0; k < ru.n_sym; ++k) {
+            ru.sym_lo[k] = mg[k].first;
+            ru.sym_hi[k] = mg[k].second;
+        }
+        out.push_back(ru);
+    }
+    return 0;
+}
+
+// (re)derive the partition and, when the symmetric path applies, its rules.  Called at create and comm_init.
+int setup_partition(steps_b200_engine *e, bool want_sym) {
+    e->sym = false;
+    e->h_rules.clear();
+    steps_b200_partition(e->n, e->nranks, e->rank, &e->i_lo, &e->i_hi);
+    if (!want_sym || e->real_bytes != 8 || e->p.topology != STEPS_TOPO_R3) return 0;
+    const SymVariant sv = SYM_VARIANTS[sym_variant()];
+    const int ib = sv.R * sv.threads;
+    int lo, hi;
+    std::vector<SymRule> rules;
+    if (build_sym_rules(e->n, e->nranks, e->rank, ib, TJ, rules, &lo, &hi)) return 0;  // geometry too small: one-sided path
+    e->sym = true;
+    e->sym_ib = ib;
+    e->i_lo = lo;
+    e->i_hi = hi;
+    e->h_rules.swap(rules);
+    if (e->d_rules) {
+        CU_TRY(cudaFree(e->d_rules));
+        e->d_rules = nullptr;
+    }
+    CU_TRY(cudaMalloc(&e->d_rules, e->h_rules.size() * sizeof(SymRule)));
+    CU_TRY(cudaMemcpy(e->d_rules, e->h_rules.data(), e->h_rules.size() * sizeof(SymRule), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// rows [lo, hi) owned by rank r under the partition in force on this engine
+void engine_partition(const steps_b200_engine *e, int r, int *lo, int *hi) {
+    if (e->sym) {
+        const int nb_total = (e->n + e->sym_ib - 1) / e->sym_ib;
+        int a, b;
+        sym_block_range(nb_total, e->nranks, r, a, b);
+        *lo = std::min(a * e->sym_ib, e->n);
+        *hi = std::min(b * e->sym_ib, e->n);
+    } else {
+        steps_b200_partition(e->n, e->nranks, r, lo, hi);
+    }
+}
+
+// the symmetric path serves calls for exactly the engine's own rows (all ranks call it collectively)
+bool sym_call(const steps_b200_engine *e, int id_min, int n_i) {
+    return e->sym && id_min == e->i_lo && n_i == e->i_hi - e->i_lo && n_i > 0;
+}
+
+Plan sym_plan(const steps_b200_engine *e, int n_i) {
+    const SymVariant sv = SYM_VARIANTS[sym_variant()];
+    Plan p{};
+    p.ib_size = sv.R * sv.threads;
+    p.n_ib = (n_i + p.ib_size - 1) / p.ib_size;
+    p.n_tiles = e->n_tiles;
+    p.slots = e->num_sms * sv.minb;
+    p.tiles_per_chunk = std::max(MIN_TILES_PER_CHUNK, (p.n_tiles + SYM_TARGET_CHUNKS - 1) / SYM_TARGET_CHUNKS);
+    p.n_chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+    p.ctas = p.n_ib * p.n_chunks;
+    return p;
 }
 
 Plan plan_for(const steps_b200_engine *e, int n_i) {
@@ -492,7 +656,84 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     CU_TRY(cudaEventRecord(e->ev[5], e->stream));
     // deterministic chunk reduction + background term
     reduce_kernel<T><<<(n_i + 255) / 256, 256, 0, e->stream>>>(static_cast<const T *>(e->d_fpart), pl.n_chunks, n_i, n_i, id_min,
-                                                                static_cast<const T *>(e->d_x), static_cast<T *>(e->d_F), e->tp);
+                                                                static_cast<const T *>(e->d_x), static_cast<T *>(e->d_F), e->tp,
+                                                                static_cast<const T *>(nullptr), (size_t)0);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+
+// Force evaluation of the engine's own rows by the action-reaction kernel: passes over groups of i-blocks (bounded
+// j-side partial buffer), each pass = pair kernel + j-side row reduction; then (multi-GPU) one all-reduce of the
+// j-side sums, then the usual chunk reduction, which also subtracts the j-side sum and adds the background term.
+int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
+    const SymVariant sv = SYM_VARIANTS[sym_variant()];
+    const Plan pl = sym_plan(e, n_i);
+    plan_out = pl;
+    if ((int)e->h_rules.size() != pl.n_ib) return fail("symmetric path: rule table does not match the i-range");
+    const size_t need = (size_t)pl.n_chunks * 3 * (size_t)n_i * sizeof(double);
+    if (need > e->fpart_bytes) {
+        if (e->d_fpart) CU_TRY(cudaFree(e->d_fpart));
+        e->d_fpart = nullptr;
+        e->fpart_bytes = 0;
+        CU_TRY(cudaMalloc(&e->d_fpart, need));
+        e->fpart_bytes = need;
+    }
+    const size_t row_bytes = (size_t)3 * e->n_pad * sizeof(double);
+    if (!e->d_fsym) CU_TRY(cudaMalloc(&e->d_fsym, row_bytes));
+    if (!e->d_gpart) {
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = std::min((size_t)16 << 30, free_b / 3);
+        if (const char *s = getenv("STEPS_B200_SYM_GPART_MB")) budget = (size_t)atoll(s) << 20;
+        size_t rows = std::max<size_t>(1, budget / row_bytes);
+        rows = std::min<size_t>(rows, (size_t)pl.n_ib);
+        CU_TRY(cudaMalloc(&e->d_gpart, rows * row_bytes));
+        e->gpart_bytes = rows * row_bytes;
+    }
+    const int rows = (int)(e->gpart_bytes / row_bytes);
+    CU_TRY(cudaMemsetAsync(e->d_fsym, 0, row_bytes, e->stream));
+    SymLaunchArgs sa{};
+    sa.a.jrec = e->d_jrec;
+    sa.a.tinfo = e->d_tinfo;
+    sa.a.fpart = e->d_fpart;
+    sa.a.id_min = id_min;
+    sa.a.n_i = n_i;
+    sa.a.tiles_per_chunk = pl.tiles_per_chunk;
+    sa.a.n_tiles = pl.n_tiles;
+    sa.a.n_j = e->n;
+    sa.a.fstride = n_i;
+    sa.rules = e->d_rules;
+    sa.gpart = e->d_gpart;
+    sa.n_pad = e->n_pad;
+    const size_t smem = (size_t)F64_STAGES * (F64_TJ * sizeof(JRec64) + sizeof(TileInfo64)) + (size_t)(sv.threads / 32) * sizeof(WarpBounds64) +
+                        (size_t)2 * (sv.threads / 32) * 3 * F64_TJ * sizeof(double) + (size_t)4 * F64_TJ * sizeof(double) +
+                        2 * F64_STAGES * sizeof(uint64_t);
+    CU_TRY(cudaEventRecord(e->ev[4], e->stream));
+    for (int b0 = 0; b0 < pl.n_ib; b0 += rows) {
+        const int nb = std::min(rows, pl.n_ib - b0);
+        sa.a.n_ib = nb;
+        sa.b0 = b0;
+#define LAUNCH_SYM(K)                                                                                                  \
+    case K: {                                                                                                          \
+        auto kern = force_r3_f64_sym_kernel<SYM_VARIANTS[K].R, SYM_VARIANTS[K].threads, F64_TJ, F64_STAGES, SYM_VARIANTS[K].minb>; \
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        kern<<<nb * pl.n_chunks, SYM_VARIANTS[K].threads, smem, e->stream>>>(sa);                                      \
+    } break;
+        switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) }
+#undef LAUNCH_SYM
+        e->launches++;
+        CU_TRY(cudaGetLastError());
+        reduce_sym_kernel<<<(e->n_pad + 255) / 256, 256, 0, e->stream>>>(e->d_gpart, e->d_rules, b0, nb, e->n_pad, TJ, e->d_fsym);
+        e->launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaEventRecord(e->ev[5], e->stream));
+    if (e->nranks > 1) NCCL_TRY(g_nccl.AllReduce(e->d_fsym, e->d_fsym, (size_t)3 * e->n_pad, ncclFloat64, ncclSum, e->comm, e->stream));
+    reduce_kernel<double><<<(n_i + 255) / 256, 256, 0, e->stream>>>(static_cast<const double *>(e->d_fpart), pl.n_chunks, n_i, n_i, id_min,
+                                                                     static_cast<const double *>(e->d_x), static_cast<double *>(e->d_F), e->tp,
+                                                                     e->d_fsym, (size_t)e->n_pad);
     e->launches++;
     CU_TRY(cudaGetLastError());
     return 0;
@@ -526,7 +767,9 @@ int forces_impl(steps_b200_engine *e, int id_min, int id_max) {
     if (pack(e)) return 1;
     Plan pl;
     const int n_i = id_max - id_min + 1;
-    int rc = (e->real_bytes == 8) ? launch_pair<double>(e, id_min, n_i, pl) : launch_pair<float>(e, id_min, n_i, pl);
+    int rc;
+    if (sym_call(e, id_min, n_i)) rc = launch_pair_sym(e, id_min, n_i, pl);
+    else rc = (e->real_bytes == 8) ? launch_pair<double>(e, id_min, n_i, pl) : launch_pair<float>(e, id_min, n_i, pl);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(e->ev[1], e->stream));
     return 0;
@@ -557,7 +800,7 @@ int gather_positions(steps_b200_engine *e) {
     NCCL_TRY(g_nccl.GroupStart());
     for (int r = 0; r < e->nranks; ++r) {
         int lo, hi;
-        steps_b200_partition(e->n, e->nranks, r, &lo, &hi);
+        engine_partition(e, r, &lo, &hi);
         char *ptr = static_cast<char *>(e->d_x) + (size_t)3 * lo * e->real_bytes;
         NCCL_TRY(g_nccl.Broadcast(ptr, ptr, (size_t)3 * (hi - lo), dt, r, e->comm, e->stream));
     }
@@ -636,7 +879,7 @@ extern "C" int steps_b200_engine_create(steps_b200_engine **out, const steps_b20
     for (auto &ev : e->ev) E_TRY(cudaEventCreate(&ev));
     for (auto &ev : e->marks) E_TRY(cudaEventCreate(&ev));
 #undef E_TRY
-    if (upload_tables(e)) {
+    if (upload_tables(e) || setup_partition(e, sym_env_default())) {
         steps_b200_engine_destroy(e);
         return 1;
     }
@@ -650,7 +893,7 @@ extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag};
+    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (e->h_errmax) cudaFreeHost(e->h_errmax);
@@ -660,6 +903,33 @@ extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
         if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
+}
+
+extern "C" int steps_b200_engine_set_symmetric(steps_b200_engine *e, int on) {
+    if (!e) return fail("engine is NULL");
+    if (e->comm) return fail("set_symmetric must precede comm_init");
+    DeviceGuard dg_;
+    CU_TRY(cudaSetDevice(e->device));
+    return setup_partition(e, on != 0);
+}
+
+extern "C" int steps_b200_engine_is_symmetric(steps_b200_engine *e) { return (e && e->sym) ? 1 : 0; }
+
+extern "C" int steps_b200_engine_range(steps_b200_engine *e, int *i_lo, int *i_hi) {
+    if (!e || !i_lo || !i_hi) return fail("engine or output is NULL");
+    *i_lo = e->i_lo;
+    *i_hi = e->i_hi;
+    return 0;
+}
+
+extern "C" int steps_b200_sym_rules(int n, int nranks, int rank, int ib_size, int *i_lo, int *i_hi, int *rules_out, int max_blocks) {
+    if (n <= 0 || nranks < 1 || rank < 0 || rank >= nranks || ib_size <= 0) return -1;
+    std::vector<SymRule> rules;
+    if (build_sym_rules(n, nranks, rank, ib_size, TJ, rules, i_lo, i_hi)) return -1;
+    if ((int)rules.size() > max_blocks) return -1;
+    static_assert(sizeof(SymRule) == 16 * sizeof(int), "rule = 16 ints");
+    if (rules_out) memcpy(rules_out, rules.data(), rules.size() * sizeof(SymRule));
+    return (int)rules.size();
 }
 
 extern "C" int steps_b200_nccl_unique_id(void *id128) {
@@ -676,11 +946,11 @@ extern "C" int steps_b200_engine_comm_init(steps_b200_engine *e, const void *id1
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank/nranks");
     e->rank = rank;
     e->nranks = nranks;
-    steps_b200_partition(e->n, nranks, rank, &e->i_lo, &e->i_hi);
-    if (nranks == 1) return 0;
-    if (nccl_load()) return 1;
     DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
+    if (setup_partition(e, e->sym || sym_env_default())) return 1;
+    if (nranks == 1) return 0;
+    if (nccl_load()) return 1;
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     NCCL_TRY(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
@@ -863,7 +1133,7 @@ extern "C" int steps_b200_engine_sync(steps_b200_engine *e) {
 
 extern "C" int steps_b200_engine_launch_shape(steps_b200_engine *e, int id_min, int id_max, int *out4) {
     if (!e) return fail("engine is NULL");
-    Plan pl = plan_for(e, id_max - id_min + 1);
+    Plan pl = sym_call(e, id_min, id_max - id_min + 1) ? sym_plan(e, id_max - id_min + 1) : plan_for(e, id_max - id_min + 1);
     out4[0] = pl.ib_size;
     out4[1] = pl.n_chunks;
     out4[2] = pl.ctas;
@@ -1061,8 +1331,8 @@ extern "C" int steps_b200_group_upload(steps_b200_group *g, const void *x, const
 
 extern "C" int steps_b200_group_forces(steps_b200_group *g) {
     if (!g) return fail("group is NULL");
-    for (auto *e : g->eng)
-        if (forces_impl(e, e->i_lo, e->i_hi - 1)) return 1;
+    // one host thread per device: the symmetric path ends in an NCCL all-reduce, which every rank must enter concurrently
+    if (group_parallel(g, [&](int d) { return forces_impl(g->eng[d], g->eng[d]->i_lo, g->eng[d]->i_hi - 1); })) return 1;
     for (auto *e : g->eng)
         if (steps_b200_engine_sync(e)) return 1;
     return 0;

@@ -1,0 +1,395 @@
+// pair_r3_sym.cuh -- action-reaction (Newton's third law) R^3 FP64 pair kernel.
+//
+// Same force law as pair_r3.cuh / forces() (forces.cc:510-577): F_i = sum_j m_j w(r_ij, s_i+s_j) (x_j - x_i).
+// w and d = x_j - x_i are symmetric / antisymmetric in (i, j), so one evaluation of g = w(r_ij) and d serves
+// BOTH particles:   F_i += m_j g d    and    F_j -= m_i g d.
+// The one-sided kernel spends 15 FP64-pipe instructions per DIRECTED pair (the pipe that bounds this path); this
+// kernel spends 20 per UNORDERED pair = 10 per directed pair:
+//     3 DADD (d), DMUL + 2 DFMA (r2), MUFU seed, t = y0^2, e = fma(-r2,t,1), c = t y0,
+//     q = fma(fma(e,1.875,1.5),e,1), g = c q, wi = g m_j, wj = g m_i, 3 DFMA into F_i, 3 DFMA into the j accumulator.
+//
+// How the j-side sum is formed without atomics (deterministic):
+//   * a warp holds 32*R i-particles in registers (R per lane) and walks a j-tile in groups of 32 records;
+//   * inside a group the 32 records VISIT the lanes systolically: at step s lane l works on record (l+s) mod 32 and
+//     owns that record's accumulator (3 doubles), which rotates one lane per step by warp shuffle; after 32 steps each
+//     record has met all 32*R i-particles of the warp and its accumulator is back in lane l = record index;
+//   * the warps of a CTA deposit their accumulators in shared memory, the CTA adds them in warp order and writes one
+//     partial row per (i-block, j-tile) to global memory; a reduce kernel adds the rows in i-block order.
+// Which (i-block, j-tile) combinations are evaluated is given by one SymRule per i-block: the tiles holding the
+// i-block's own particles are evaluated one-sidedly (both directions appear there, self pair included), tiles in
+// the rule's symmetric ranges are evaluated once for both sides, all other tiles are skipped (their pairs are
+// evaluated by the CTA of the other block).  The host builds the rules so that every unordered pair of the whole
+// job is covered exactly once (engine.cu: build_sym_rules; multi-GPU: ring assignment of block pairs).
+#pragma once
+#include "pair_r3.cuh"
+
+namespace steps {
+
+constexpr int SYM_MAX_RANGES = 5;
+struct __align__(16) SymRule {
+    int diag_lo, diag_hi;  // tiles [diag_lo, diag_hi): the i-block's own particles (one-sided evaluation)
+    int n_sym;             // number of symmetric tile ranges
+    int sym_lo[SYM_MAX_RANGES], sym_hi[SYM_MAX_RANGES];
+    int pad[3];
+};
+static_assert(sizeof(SymRule) == 64, "SymRule layout");
+
+// 0 = skip, 1 = one-sided (diagonal), 2 = symmetric
+__host__ __device__ __forceinline__ int sym_tile_class(const SymRule &r, int t) {
+    if (t >= r.diag_lo && t < r.diag_hi) return 1;
+    for (int k = 0; k < r.n_sym; ++k)
+        if (t >= r.sym_lo[k] && t < r.sym_hi[k]) return 2;
+    return 0;
+}
+
+struct SymLaunchArgs {
+    R3LaunchArgs a;        // jrec/tinfo/fpart/id_min/n_i/tiles_per_chunk/n_tiles/n_j/fstride as for the one-sided kernel;
+                           // a.n_ib = number of i-blocks in THIS launch (a pass)
+    const SymRule *rules;  // one per local i-block (index 0 = the block starting at id_min)
+    double *gpart;         // j-side partial rows: [i-block of the pass][3][n_pad]
+    int b0;                // first local i-block of this pass
+    int n_pad;             // n_tiles * TJ
+};
+
+// exact softened kernel for one flagged pair (rare; out of line)
+__device__ __noinline__ double sym_exact_w(double r2, double beta) { return softened_w<double>(sqrt(r2), beta); }
+
+#define STEPS_PAIR_SYM_CORE(XJ, YJ, ZJ, r, YH_EXPR)                                        \
+    const double dx = (XJ) - xi[r];                                                        \
+    const double dy = (YJ) - yi[r];                                                        \
+    const double dz = (ZJ) - zi[r];                                                        \
+    const double dx2 = dx * dx;                                                            \
+    double r2 = fma(dy, dy, dx2);                                                          \
+    r2 = fma(dz, dz, r2);                                                                  \
+    int yh = __double2hiint(rsqrt_seed(r2));                                               \
+    YH_EXPR;                                                                               \
+    const double y0 = __hiloint2double(yh, __double2loint(dx2));                           \
+    const double tt = y0 * y0;                                                             \
+    const double e = fma(-r2, tt, 1.0);                                                    \
+    const double c = tt * y0;                                                              \
+    double q = fma(e, 1.875, 1.5);                                                         \
+    q = fma(q, e, 1.0);                                                                    \
+    const double g = c * q;
+
+// One symmetric (i-warp x j-tile) block.  CHECKED = false: every pair is provably outside the softening radius (no
+// per-pair test at all); true: pairs with hi(r2) <= thr[r] are masked out of the fast arithmetic (seed := 0 => g = 0
+// exactly) and re-evaluated with the reference's exact branches before the accumulators rotate.
+template <int R, int TJ, int THREADS, bool CHECKED>
+__device__ __forceinline__ void sym_tile(const JRec64 *__restrict__ T, const double *__restrict__ soa, int lane, int tid,
+                                         const double (&xi)[R], const double (&yi)[R],
+                                         const double (&zi)[R], const double (&mi)[R], double (&ax)[R], double (&ay)[R], double (&az)[R],
+                                         const int (&thr)[R], double *__restrict__ slot, const JRec64 *__restrict__ jrec, int id_min,
+                                         int n_i, int ib) {
+    constexpr int IB = THREADS * R;
+    for (int g0 = 0; g0 < TJ; g0 += 32) {
+        double vx = 0.0, vy = 0.0, vz = 0.0;
+        const JRec64 *__restrict__ G = T + g0;
+        // per-lane records come from the SoA copy of the tile (x | y | z | m, TJ doubles each): 32 lanes read 32
+        // consecutive doubles, conflict-free, where the 64-byte AoS records would collide 16-way
+        const double *__restrict__ S = soa + g0;
+        double nx = S[lane], ny = S[TJ + lane], nz = S[2 * TJ + lane], nm = S[3 * TJ + lane];
+#pragma unroll 1
+        for (int s2 = 0; s2 < 32; ++s2) {
+            const double2 xy = make_double2(nx, ny), zm = make_double2(nz, nm);
+            const int jn = (lane + s2 + 1) & 31;  // record of the next step (prefetched)
+            nx = S[jn]; ny = S[TJ + jn]; nz = S[2 * TJ + jn]; nm = S[3 * TJ + jn];
+            int ymin = 0x7fffffff;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                STEPS_PAIR_SYM_CORE(xy.x, xy.y, zm.x, r, if (CHECKED) { yh = (__double2hiint(r2) <= thr[r]) ? 0 : yh; ymin = min(ymin, yh); })
+                const double wi = g * zm.y;
+                const double wj = g * mi[r];
+                ax[r] = fma(wi, dx, ax[r]);
+                ay[r] = fma(wi, dy, ay[r]);
+                az[r] = fma(wi, dz, az[r]);
+                vx = fma(wj, dx, vx);
+                vy = fma(wj, dy, vy);
+                vz = fma(wj, dz, vz);
+            }
+            if (CHECKED) {
+                if (ymin == 0) {
+                    // rare: some pair of this step lies inside the softening radius (or coincides): exact branches
+                    const double sj = G[(lane + s2) & 31].s;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double dx = xy.x - xi[r], dy = xy.y - yi[r], dz = zm.x - zi[r];
+                        double r2 = dx * dx;
+                        r2 = fma(dy, dy, r2);
+                        r2 = fma(dz, dz, r2);
+                        if (__double2hiint(r2) <= thr[r]) {
+                            int il = ib * IB + r * THREADS + tid;
+                            il = il < n_i ? il : n_i - 1;
+                            const double w = sym_exact_w(r2, jrec[id_min + il].s + sj);
+                            const double wi = w * zm.y, wj = w * mi[r];
+                            ax[r] = fma(wi, dx, ax[r]);
+                            ay[r] = fma(wi, dy, ay[r]);
+                            az[r] = fma(wi, dz, az[r]);
+                            vx = fma(wj, dx, vx);
+                            vy = fma(wj, dy, vy);
+                            vz = fma(wj, dz, vz);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // the accumulator follows its record: lane l takes over the record lane l+1 just worked on
+            vx = __shfl_sync(0xffffffffu, vx, (lane + 1) & 31);
+            vy = __shfl_sync(0xffffffffu, vy, (lane + 1) & 31);
+            vz = __shfl_sync(0xffffffffu, vz, (lane + 1) & 31);
+        }
+        // after 32 rotations lane l holds the accumulator of record g0 + l
+        slot[g0 + lane] = vx;
+        slot[TJ + g0 + lane] = vy;
+        slot[2 * TJ + g0 + lane] = vz;
+    }
+}
+
+template <int R, int THREADS, int TJ, int STAGES, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_sym_kernel(const SymLaunchArgs sa) {
+    constexpr int NWARPS = THREADS / 32;
+    constexpr int JB = 16;
+    constexpr int IB = THREADS * R;
+    static_assert(THREADS >= TJ && TJ % 32 == 0 && IB % TJ == 0, "shape");
+    const R3LaunchArgs &a = sa.a;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    JRec64 *tiles = reinterpret_cast<JRec64 *>(smem_raw);
+    TileInfo64 *tinfo_s = reinterpret_cast<TileInfo64 *>(smem_raw + (size_t)STAGES * TJ * sizeof(JRec64));
+    WarpBounds64 *wb_s = reinterpret_cast<WarpBounds64 *>(tinfo_s + STAGES);
+    double *slots = reinterpret_cast<double *>(wb_s + NWARPS);  // [2][NWARPS][3][TJ]
+    double *soa = slots + 2 * NWARPS * 3 * TJ;                   // [4][TJ]: x | y | z | m of the current symmetric tile
+    uint64_t *full = reinterpret_cast<uint64_t *>(soa + 4 * TJ);
+    uint64_t *empty = full + STAGES;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int jc = blockIdx.x / a.n_ib;  // chunk-major
+    const int gb = blockIdx.x - jc * a.n_ib;  // i-block within the pass
+    const int ib = sa.b0 + gb;                // local i-block
+    const SymRule *__restrict__ rule = sa.rules + ib;  // read through L1 when needed: a register copy would cost 13 registers
+    // active tile range of this CTA: hull of (diag, symmetric ranges) intersected with the chunk
+    int ta, tb;
+    {
+        const int c0 = jc * a.tiles_per_chunk;
+        const int c1 = min(c0 + a.tiles_per_chunk, a.n_tiles);
+        ta = 0x7fffffff;
+        tb = -1;
+        {
+            const int lo = max(rule->diag_lo, c0), hi = min(rule->diag_hi, c1);
+            if (lo < hi) { ta = min(ta, lo); tb = max(tb, hi); }
+        }
+        for (int k = 0; k < rule->n_sym; ++k) {
+            const int lo = max(rule->sym_lo[k], c0), hi = min(rule->sym_hi[k], c1);
+            if (lo < hi) { ta = min(ta, lo); tb = max(tb, hi); }
+        }
+    }
+    double *__restrict__ fp = static_cast<double *>(a.fpart) + (size_t)jc * 3 * a.fstride;
+    if (tb <= ta) {
+        // nothing to do for this (i-block, chunk): the partial sums of the chunk are still read by the reduce kernel
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int il = ib * IB + r * THREADS + tid;
+            if (il < a.n_i) {
+                fp[il] = 0.0;
+                fp[a.fstride + il] = 0.0;
+                fp[2 * (size_t)a.fstride + il] = 0.0;
+            }
+        }
+        return;
+    }
+    const int t0 = ta, nt = tb - ta;
+    const JRec64 *__restrict__ jrec = static_cast<const JRec64 *>(a.jrec);
+    const TileInfo64 *__restrict__ tinfo = static_cast<const TileInfo64 *>(a.tinfo);
+    constexpr uint32_t TILE_TX = TJ * sizeof(JRec64) + sizeof(TileInfo64);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NWARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int npre = nt < STAGES ? nt : STAGES;
+        for (int t = 0; t < npre; ++t) {
+            mbar_arrive_expect_tx(&full[t], TILE_TX);
+            tma_load_1d(tiles + (size_t)t * TJ, jrec + (size_t)(t0 + t) * TJ, TJ * sizeof(JRec64), &full[t]);
+            tma_load_1d(tinfo_s + t, tinfo + (t0 + t), sizeof(TileInfo64), &full[t]);
+        }
+    }
+
+    double xi[R], yi[R], zi[R], mi[R], ax[R], ay[R], az[R];
+    float si_up[R];
+    {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, rlo = 1e300, rhi = 0.0;
+        float smx = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int il0 = ib * IB + r * THREADS + tid;
+            const int il = il0 < a.n_i ? il0 : a.n_i - 1;
+            const JRec64 me = jrec[a.id_min + il];
+            xi[r] = me.x; yi[r] = me.y; zi[r] = me.z;
+            mi[r] = il0 < a.n_i ? me.m : 0.0;  // a clamped duplicate must not act on the j side
+            si_up[r] = __double2float_ru(me.s);
+            ax[r] = ay[r] = az[r] = 0.0;
+            lo[0] = fmin(lo[0], me.x); hi[0] = fmax(hi[0], me.x);
+            lo[1] = fmin(lo[1], me.y); hi[1] = fmax(hi[1], me.y);
+            lo[2] = fmin(lo[2], me.z); hi[2] = fmax(hi[2], me.z);
+            const double rr = sqrt(me.x * me.x + me.y * me.y + me.z * me.z);
+            rlo = fmin(rlo, rr); rhi = fmax(rhi, rr);
+            smx = fmaxf(smx, si_up[r]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+                hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+            }
+            rlo = fmin(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
+            rhi = fmax(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
+            smx = fmaxf(smx, __shfl_xor_sync(0xffffffffu, smx, o));
+        }
+        if (lane == 0) {
+            WarpBounds64 &wb = wb_s[warp];
+            wb.lo[0] = lo[0]; wb.lo[1] = lo[1]; wb.lo[2] = lo[2];
+            wb.hi[0] = hi[0]; wb.hi[1] = hi[1]; wb.hi[2] = hi[2];
+            wb.rlo = rlo; wb.rhi = rhi; wb.smax = (double)smx; wb.pad = 0.0;
+        }
+        __syncwarp();
+    }
+    const WarpBounds64 *__restrict__ wb = wb_s + warp;
+    int nsym = 0;  // symmetric tiles processed so far (selects the slot buffer)
+
+    for (int t = 0; t < nt; ++t) {
+        const int s = t % STAGES;
+        const uint32_t ph = (uint32_t)(t / STAGES) & 1u;
+        if (tid == 0 && t >= 1 && (t - 1 + STAGES) < nt) {
+            const int sp = (t - 1) % STAGES;
+            const uint32_t php = (uint32_t)((t - 1) / STAGES) & 1u;
+            mbar_wait(&empty[sp], php);
+            mbar_arrive_expect_tx(&full[sp], TILE_TX);
+            tma_load_1d(tiles + (size_t)sp * TJ, jrec + (size_t)(t0 + t - 1 + STAGES) * TJ, TJ * sizeof(JRec64), &full[sp]);
+            tma_load_1d(tinfo_s + sp, tinfo + (t0 + t - 1 + STAGES), sizeof(TileInfo64), &full[sp]);
+        }
+        mbar_wait(&full[s], ph);
+        const JRec64 *__restrict__ T = tiles + (size_t)s * TJ;
+        const int cls = sym_tile_class(*rule, t0 + t);  // CTA-uniform
+        if (cls != 0) {
+            const double smax = T[0].smax;
+            bool far;
+            {
+                const TileInfo64 *__restrict__ ti = tinfo_s + s;
+                double gap2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double gp = fmax(fmax(wb->lo[k] - ti->hi[k], ti->lo[k] - wb->hi[k]), 0.0);
+                    gap2 = fma(gp, gp, gap2);
+                }
+                const double rg = fmax(wb->rlo - ti->rhi, ti->rlo - wb->rhi);
+                const double b = (wb->smax + smax) * 1.000001;
+                far = (gap2 > b * b) || (rg > b);
+            }
+            int thr[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double b = (double)si_up[r] + smax;
+                thr[r] = far ? -1 : __double2hiint(b * b) + 1;  // far tiles: nothing is ever flagged
+            }
+            if (cls == 1) {
+                // ---- the i-block's own tiles: one-sided evaluation, checked loop (pair_r3.cuh near branch) ----
+                for (int j0 = 0; j0 < TJ; j0 += JB) {
+                    int ymin = 0x7fffffff;
+#pragma unroll 1
+                    for (int jj = 0; jj < JB; ++jj) {
+                        const double2 xy = *reinterpret_cast<const double2 *>(&T[j0 + jj].x);
+                        const double2 zm = *reinterpret_cast<const double2 *>(&T[j0 + jj].z);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            STEPS_PAIR_SYM_CORE(xy.x, xy.y, zm.x, r, yh = (__double2hiint(r2) <= thr[r]) ? 0 : yh; ymin = min(ymin, yh))
+                            const double wi = g * zm.y;
+                            ax[r] = fma(wi, dx, ax[r]);
+                            ay[r] = fma(wi, dy, ay[r]);
+                            az[r] = fma(wi, dz, az[r]);
+                        }
+                    }
+                    if (ymin == 0) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            int il = ib * IB + r * THREADS + tid;
+                            il = il < a.n_i ? il : a.n_i - 1;
+                            const double3 f = near_pairs_f64(T + j0, JB, xi[r], yi[r], zi[r], jrec[a.id_min + il].s, thr[r]);
+                            ax[r] += f.x; ay[r] += f.y; az[r] += f.z;
+                        }
+                    }
+                }
+            } else {
+                // ---- symmetric tile: systolic visit of 32 records per group ----
+                double *__restrict__ slot = slots + ((size_t)(nsym & 1) * NWARPS + warp) * 3 * TJ;
+                // AoS -> SoA copy of the tile's hot fields.  Every warp left the previous symmetric tile's loop before the
+                // __syncthreads that preceded its row combine, so the buffer is free to overwrite here.
+                if (tid < TJ) {
+                    const double2 xy = *reinterpret_cast<const double2 *>(&T[tid].x);
+                    const double2 zm = *reinterpret_cast<const double2 *>(&T[tid].z);
+                    soa[tid] = xy.x;
+                    soa[TJ + tid] = xy.y;
+                    soa[2 * TJ + tid] = zm.x;
+                    soa[3 * TJ + tid] = zm.y;
+                }
+                __syncthreads();
+                if (far)
+                    sym_tile<R, TJ, THREADS, false>(T, soa, lane, tid, xi, yi, zi, mi, ax, ay, az, thr, slot, jrec, a.id_min, a.n_i, ib);
+                else
+                    sym_tile<R, TJ, THREADS, true>(T, soa, lane, tid, xi, yi, zi, mi, ax, ay, az, thr, slot, jrec, a.id_min, a.n_i, ib);
+                __syncthreads();
+                if (tid < TJ) {
+                    const double *__restrict__ sb = slots + (size_t)(nsym & 1) * NWARPS * 3 * TJ;
+                    double *__restrict__ gp = sa.gpart + (size_t)gb * 3 * sa.n_pad + (size_t)(t0 + t) * TJ + tid;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int w = 0; w < NWARPS; ++w) v += sb[((size_t)w * 3 + c) * TJ + tid];
+                        gp[(size_t)c * sa.n_pad] = v;
+                    }
+                }
+                ++nsym;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int il = ib * IB + r * THREADS + tid;
+        if (il < a.n_i) {
+            fp[il] = ax[r];
+            fp[a.fstride + il] = ay[r];
+            fp[2 * (size_t)a.fstride + il] = az[r];
+        }
+    }
+}
+
+// j-side reduction of one pass: fsym[c][j] += sum over the pass's i-blocks (in block order) of the rows that hold a
+// symmetric contribution for j's tile.  One thread per j.
+__global__ void reduce_sym_kernel(const double *__restrict__ gpart, const SymRule *__restrict__ rules, int b0, int nb, int n_pad,
+                                  int tj, double *__restrict__ fsym) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_pad) return;
+    const int t = j / tj;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int g = 0; g < nb; ++g) {
+        if (sym_tile_class(rules[b0 + g], t) == 2) {
+            const double *__restrict__ row = gpart + (size_t)g * 3 * n_pad + j;
+            sx += row[0];
+            sy += row[(size_t)n_pad];
+            sz += row[2 * (size_t)n_pad];
+        }
+    }
+    fsym[j] += sx;
+    fsym[(size_t)n_pad + j] += sy;
+    fsym[2 * (size_t)n_pad + j] += sz;
+}
+
+}  // namespace steps

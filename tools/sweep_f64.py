@@ -10,12 +10,14 @@ def child(n):
     REAL = np.float32 if os.environ.get("SWEEP_REAL", "f64") == "f32" else np.float64
     c = ic.compactified_r3(n, 224, max(1, int(0.854 * n / 122)), 20242, REAL)
     eng = sb.Engine(c.g, 0)
+    if os.environ.get("SWEEP_SYM"):
+        eng.set_symmetric(True)
     eng.upload(c.x, c.v)
     ms = []
     for _ in range(4):
         eng.forces(); eng.sync(); ms.append(eng.pair_kernel_ms())
     F = eng.download_forces(0, 9)
-    print(json.dumps({"variant": int(os.environ.get("STEPS_B200_F32_VARIANT" if REAL == np.float32 else "STEPS_B200_F64_VARIANT", "0")), "real": REAL.__name__, "ms": min(ms[1:]), "pairs_per_s": n * float(n) / (min(ms[1:]) * 1e-3),
+    print(json.dumps({"sym": bool(eng.symmetric), "sym_variant": os.environ.get("STEPS_B200_SYM_VARIANT", "0"), "variant": int(os.environ.get("STEPS_B200_F32_VARIANT" if REAL == np.float32 else "STEPS_B200_F64_VARIANT", "0")), "real": REAL.__name__, "ms": min(ms[1:]), "pairs_per_s": n * float(n) / (min(ms[1:]) * 1e-3),
                       "shape": eng.launch_shape(0, n - 1), "F0": float(F[0])}))
 
 if __name__ == "__main__":

@@ -124,6 +124,12 @@ int steps_b200_engine_set_symmetric(steps_b200_engine *e, int on);
 int steps_b200_engine_is_symmetric(steps_b200_engine *e);
 int steps_b200_engine_range(steps_b200_engine *e, int *i_lo, int *i_hi);
 int steps_b200_sym_rules(int n, int nranks, int rank, int ib_size, int *i_lo, int *i_hi, int *rules_out, int max_blocks);
+/* Test hooks (tests/test_gpu_sym.py): one GPU plays every rank of a P-GPU action-reaction job in turn.
+ * debug_set_rank gives the engine the rows and rules of `rank` of `nranks` without a communicator (its evaluation
+ * then skips the all-reduce); debug_fsym reads the engine's j-side sums ([3][n_pad] doubles) and/or replaces them by
+ * the caller's total and redoes the final reduction. */
+int steps_b200_engine_debug_set_rank(steps_b200_engine *e, int rank, int nranks, int symmetric);
+int steps_b200_engine_debug_fsym(steps_b200_engine *e, double *fsym_out, const double *fsym_in, int *n_pad_out);
 
 /* NCCL bootstrap for one-process-per-GPU runs: rank 0 calls unique_id() and ships the 128 bytes to
  * the others by any means (MPI_Bcast in StePS, torch.distributed in bench.py); then every rank

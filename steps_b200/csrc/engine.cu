@@ -664,6 +664,16 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
 }
 
 
+// last phase of the action-reaction evaluation: chunk sums of the i side - j-side sums + background term -> F
+int finish_pair_sym(steps_b200_engine *e, int id_min, int n_i, const Plan &pl) {
+    reduce_kernel<double><<<(n_i + 255) / 256, 256, 0, e->stream>>>(static_cast<const double *>(e->d_fpart), pl.n_chunks, n_i, n_i, id_min,
+                                                                     static_cast<const double *>(e->d_x), static_cast<double *>(e->d_F), e->tp,
+                                                                     e->d_fsym, (size_t)e->n_pad);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
 // Force evaluation of the engine's own rows by the action-reaction kernel: passes over groups of i-blocks (bounded
 // j-side partial buffer), each pass = pair kernel + j-side row reduction; then (multi-GPU) one all-reduce of the
 // j-side sums, then the usual chunk reduction, which also subtracts the j-side sum and adds the background term.
@@ -730,13 +740,11 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         CU_TRY(cudaGetLastError());
     }
     CU_TRY(cudaEventRecord(e->ev[5], e->stream));
-    if (e->nranks > 1) NCCL_TRY(g_nccl.AllReduce(e->d_fsym, e->d_fsym, (size_t)3 * e->n_pad, ncclFloat64, ncclSum, e->comm, e->stream));
-    reduce_kernel<double><<<(n_i + 255) / 256, 256, 0, e->stream>>>(static_cast<const double *>(e->d_fpart), pl.n_chunks, n_i, n_i, id_min,
-                                                                     static_cast<const double *>(e->d_x), static_cast<double *>(e->d_F), e->tp,
-                                                                     e->d_fsym, (size_t)e->n_pad);
-    e->launches++;
-    CU_TRY(cudaGetLastError());
-    return 0;
+    // multi-GPU: the j-side sums a rank formed for other ranks' particles travel in ONE all-reduce (3 n_pad doubles).
+    // (An engine given a rank without a communicator -- the single-GPU test hook -- skips it: the test sums on the host.)
+    if (e->nranks > 1 && e->comm)
+        NCCL_TRY(g_nccl.AllReduce(e->d_fsym, e->d_fsym, (size_t)3 * e->n_pad, ncclFloat64, ncclSum, e->comm, e->stream));
+    return finish_pair_sym(e, id_min, n_i, pl);
 }
 
 int pack(steps_b200_engine *e) {
@@ -930,6 +938,43 @@ extern "C" int steps_b200_sym_rules(int n, int nranks, int rank, int ib_size, in
     static_assert(sizeof(SymRule) == 16 * sizeof(int), "rule = 16 ints");
     if (rules_out) memcpy(rules_out, rules.data(), rules.size() * sizeof(SymRule));
     return (int)rules.size();
+}
+
+// ---- test hooks of the multi-GPU action-reaction path on ONE device (tests/test_gpu_sym.py) ----
+// debug_set_rank: give the engine the rows and rules of rank `rank` of `nranks` WITHOUT a communicator; its force
+// evaluation then stops short of the all-reduce.  debug_fsym: read the engine's j-side sums ([3][n_pad] doubles), or
+// (fsym_in != NULL) replace them by the caller's total and redo the final reduction.  Together they let one GPU play
+// every rank of a P-GPU job in turn, the host standing in for the all-reduce.
+extern "C" int steps_b200_engine_debug_set_rank(steps_b200_engine *e, int rank, int nranks, int symmetric) {
+    if (!e) return fail("engine is NULL");
+    if (e->comm) return fail("debug_set_rank on an engine with a communicator");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank/nranks");
+    DeviceGuard dg_;
+    CU_TRY(cudaSetDevice(e->device));
+    e->rank = rank;
+    e->nranks = nranks;
+    return setup_partition(e, symmetric != 0);
+}
+
+extern "C" int steps_b200_engine_debug_fsym(steps_b200_engine *e, double *fsym_out, const double *fsym_in, int *n_pad_out) {
+    if (!e) return fail("engine is NULL");
+    if (n_pad_out) *n_pad_out = e->n_pad;
+    if (!fsym_out && !fsym_in) return 0;
+    if (!e->sym || !e->d_fsym) return fail("no action-reaction evaluation has run on this engine");
+    DeviceGuard dg_;
+    CU_TRY(cudaSetDevice(e->device));
+    const size_t bytes = (size_t)3 * e->n_pad * sizeof(double);
+    if (fsym_out) {
+        CU_TRY(cudaMemcpyAsync(fsym_out, e->d_fsym, bytes, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+    }
+    if (fsym_in) {
+        CU_TRY(cudaMemcpyAsync(e->d_fsym, fsym_in, bytes, cudaMemcpyHostToDevice, e->stream));
+        const int n_i = e->i_hi - e->i_lo;
+        if (finish_pair_sym(e, e->i_lo, n_i, sym_plan(e, n_i))) return 1;
+        CU_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return 0;
 }
 
 extern "C" int steps_b200_nccl_unique_id(void *id128) {

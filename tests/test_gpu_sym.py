@@ -137,6 +137,48 @@ def test_sym_kdk_steps_match_one_sided_engine():
     assert noise_err(F2, F1, S).max() < 1e-12
 
 
+@pytest.mark.parametrize("nranks", [2, 3, 4, 8])
+def test_sym_multi_rank_rules_and_kernel_on_one_gpu(nranks):
+    """one GPU plays every rank of a P-GPU job in turn (rows, rules, pair kernel, row reduction of each rank); the host
+    stands in for the all-reduce of the j-side sums.  Leaves only the NCCL call itself to the >= 2 GPU tests."""
+    import ctypes as C
+
+    from steps_b200 import _lib
+
+    c = ic.compactified_r3(20000, 64, 250, 42, d_s=105.0)
+    g = c.g
+    lib = _lib.load()
+    engines, fsyms, ranges = [], [], []
+    for r in range(nranks):
+        eng = sb.Engine(g, 0)
+        _lib.check(lib.steps_b200_engine_debug_set_rank(eng._h, r, nranks, 1))
+        assert eng.symmetric
+        eng.i_lo, eng.i_hi = eng.range()
+        ranges.append((eng.i_lo, eng.i_hi))
+        eng.upload(c.x, c.v)
+        eng.forces()
+        n_pad = C.c_int()
+        _lib.check(lib.steps_b200_engine_debug_fsym(eng._h, None, None, C.byref(n_pad)))
+        f = np.empty(3 * n_pad.value)
+        _lib.check(lib.steps_b200_engine_debug_fsym(eng._h, f.ctypes.data, None, None))
+        engines.append(eng)
+        fsyms.append(f)
+    assert ranges[0][0] == 0 and ranges[-1][1] == g.N and all(ranges[k][1] == ranges[k + 1][0] for k in range(nranks - 1))
+    total = np.sum(fsyms, axis=0)
+    F = np.empty(3 * g.N)
+    for eng, (lo, hi) in zip(engines, ranges):
+        _lib.check(lib.steps_b200_engine_debug_fsym(eng._h, None, total.ctypes.data, None))
+        F[3 * lo: 3 * hi] = eng.download_forces(lo, hi - 1)
+        eng.close()
+    Fo = pyport.forces(g, c.x, 0, g.N - 1)
+    S = pyport.force_norms(g, c.x, 0, g.N - 1)
+    ne = noise_err(F, Fo, S)
+    print(f"{nranks} ranks on one GPU: max |dF|/sum|f| = {ne.max():.3e}")
+    assert np.isfinite(F).all()
+    assert ne.max() < TOL64
+    assert np.percentile(rel_err(F, Fo), 99) < TOL64
+
+
 def test_sym_large_n_properties():
     """N = 400k zoom geometry: sampled rows against the oracle, momentum, agreement with the one-sided kernel"""
     n = 400_000

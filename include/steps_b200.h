@@ -113,8 +113,8 @@ void steps_b200_partition(int n, int nranks, int rank, int *i_lo, int *i_hi);
 /* Action-reaction evaluation of the R^3 FP64 path (pair_r3_sym.cuh): every unordered pair is evaluated once and
  * applied to both particles (F_i += m_j w d, F_j -= m_i w d), the same force law as forces() (forces.cc:510-577).
  * It serves force calls for exactly the engine's own rows; multi-GPU engines then partition rows on i-block
- * boundaries and exchange the j-side sums with one all-reduce per evaluation.  Default: environment variable
- * STEPS_B200_SYM (0/1).  set_symmetric() must precede comm_init() and is collective in spirit: every rank of a job
+ * boundaries and exchange the j-side sums with one all-reduce per evaluation.  On by default; environment variable
+ * STEPS_B200_SYM=0 turns it off.  set_symmetric() must precede comm_init() and is collective in spirit: every rank of a job
  * must make the same choice.  engine_range() returns the rows [i_lo, i_hi) the engine owns under the partition
  * in force.  sym_rules() is the host-only rule builder (no GPU needed): for rank `rank` of `nranks`, i-block size
  * ib_size (a multiple of the 128-record j-tile), it writes 16 ints per local i-block

@@ -365,12 +365,16 @@ bool tuned_s1r2(const steps_b200_engine *e) {
 
 // ---------------------------------------------------------------- action-reaction path (pair_r3_sym.cuh)
 struct SymVariant {
-    int R, threads, minb;
+    int R, threads, minb, unroll;
 };
 constexpr SymVariant SYM_VARIANTS[] = {
-    {6, 128, 2},  // 0: 253 registers, no spills; i-block 768
-    {8, 128, 2},  // 1: 255 registers, a few spills outside the hot loop; i-block 1024
-    {7, 128, 2},  // 2: i-block 896
+    {6, 128, 2, 1},  // 0: PRODUCTION.  254 registers, no spills; i-block 768
+    {8, 128, 2, 1},  // 1: 255 registers, a few spills outside the hot loop; i-block 1024
+    {7, 128, 2, 1},  // 2: i-block 896
+    {6, 128, 2, 2},  // 3: visiting steps unrolled by 2 (no register moves for the prefetched record)
+    {6, 256, 1, 1},  // 4: one 256-thread CTA per SM; i-block 1536
+    {4, 128, 3, 1},  // 5: 12 warps/SM, <= 170 registers; i-block 512
+    {6, 128, 2, 4},  // 6: visiting steps unrolled by 4
 };
 constexpr int N_SYM_VARIANTS = sizeof(SYM_VARIANTS) / sizeof(SYM_VARIANTS[0]);
 int sym_variant() {
@@ -385,8 +389,8 @@ int sym_variant() {
 bool sym_env_default() {
     static int v = -1;
     if (v < 0) {
-        const char *s = getenv("STEPS_B200_SYM");
-        v = (s && atoi(s) != 0) ? 1 : 0;
+        const char *s = getenv("STEPS_B200_SYM");  // default on; STEPS_B200_SYM=0 keeps every call on the one-sided kernel
+        v = (s && atoi(s) == 0) ? 0 : 1;
     }
     return v == 1;
 }
@@ -512,7 +516,9 @@ Plan sym_plan(const steps_b200_engine *e, int n_i) {
     p.n_ib = (n_i + p.ib_size - 1) / p.ib_size;
     p.n_tiles = e->n_tiles;
     p.slots = e->num_sms * sv.minb;
-    p.tiles_per_chunk = std::max(MIN_TILES_PER_CHUNK, (p.n_tiles + SYM_TARGET_CHUNKS - 1) / SYM_TARGET_CHUNKS);
+    int target = SYM_TARGET_CHUNKS;
+    if (const char *s = getenv("STEPS_B200_SYM_CHUNKS")) target = std::max(1, atoi(s));  // tuning knob
+    p.tiles_per_chunk = std::max(MIN_TILES_PER_CHUNK, (p.n_tiles + target - 1) / target);
     p.n_chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
     p.ctas = p.n_ib * p.n_chunks;
     return p;
@@ -727,11 +733,12 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         sa.b0 = b0;
 #define LAUNCH_SYM(K)                                                                                                  \
     case K: {                                                                                                          \
-        auto kern = force_r3_f64_sym_kernel<SYM_VARIANTS[K].R, SYM_VARIANTS[K].threads, F64_TJ, F64_STAGES, SYM_VARIANTS[K].minb>; \
+        auto kern = force_r3_f64_sym_kernel<SYM_VARIANTS[K].R, SYM_VARIANTS[K].threads, F64_TJ, F64_STAGES, SYM_VARIANTS[K].minb, \
+                                            SYM_VARIANTS[K].unroll>;                                                   \
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
         kern<<<nb * pl.n_chunks, SYM_VARIANTS[K].threads, smem, e->stream>>>(sa);                                      \
     } break;
-        switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) }
+        switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) LAUNCH_SYM(3) LAUNCH_SYM(4) LAUNCH_SYM(5) LAUNCH_SYM(6) }
 #undef LAUNCH_SYM
         e->launches++;
         CU_TRY(cudaGetLastError());

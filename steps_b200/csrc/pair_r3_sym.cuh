@@ -74,7 +74,7 @@ __device__ __noinline__ double sym_exact_w(double r2, double beta) { return soft
 // One symmetric (i-warp x j-tile) block.  CHECKED = false: every pair is provably outside the softening radius (no
 // per-pair test at all); true: pairs with hi(r2) <= thr[r] are masked out of the fast arithmetic (seed := 0 => g = 0
 // exactly) and re-evaluated with the reference's exact branches before the accumulators rotate.
-template <int R, int TJ, int THREADS, bool CHECKED>
+template <int R, int TJ, int THREADS, bool CHECKED, int UNR>
 __device__ __forceinline__ void sym_tile(const JRec64 *__restrict__ T, const double *__restrict__ soa, int lane, int tid,
                                          const double (&xi)[R], const double (&yi)[R],
                                          const double (&zi)[R], const double (&mi)[R], double (&ax)[R], double (&ay)[R], double (&az)[R],
@@ -88,7 +88,7 @@ __device__ __forceinline__ void sym_tile(const JRec64 *__restrict__ T, const dou
         // consecutive doubles, conflict-free, where the 64-byte AoS records would collide 16-way
         const double *__restrict__ S = soa + g0;
         double nx = S[lane], ny = S[TJ + lane], nz = S[2 * TJ + lane], nm = S[3 * TJ + lane];
-#pragma unroll 1
+#pragma unroll UNR
         for (int s2 = 0; s2 < 32; ++s2) {
             const double2 xy = make_double2(nx, ny), zm = make_double2(nz, nm);
             const int jn = (lane + s2 + 1) & 31;  // record of the next step (prefetched)
@@ -144,7 +144,7 @@ __device__ __forceinline__ void sym_tile(const JRec64 *__restrict__ T, const dou
     }
 }
 
-template <int R, int THREADS, int TJ, int STAGES, int MINB>
+template <int R, int THREADS, int TJ, int STAGES, int MINB, int UNR>
 __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_sym_kernel(const SymLaunchArgs sa) {
     constexpr int NWARPS = THREADS / 32;
     constexpr int JB = 16;
@@ -338,9 +338,9 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_sym_kernel(const S
                 }
                 __syncthreads();
                 if (far)
-                    sym_tile<R, TJ, THREADS, false>(T, soa, lane, tid, xi, yi, zi, mi, ax, ay, az, thr, slot, jrec, a.id_min, a.n_i, ib);
+                    sym_tile<R, TJ, THREADS, false, UNR>(T, soa, lane, tid, xi, yi, zi, mi, ax, ay, az, thr, slot, jrec, a.id_min, a.n_i, ib);
                 else
-                    sym_tile<R, TJ, THREADS, true>(T, soa, lane, tid, xi, yi, zi, mi, ax, ay, az, thr, slot, jrec, a.id_min, a.n_i, ib);
+                    sym_tile<R, TJ, THREADS, true, UNR>(T, soa, lane, tid, xi, yi, zi, mi, ax, ay, az, thr, slot, jrec, a.id_min, a.n_i, ib);
                 __syncthreads();
                 if (tid < TJ) {
                     const double *__restrict__ sb = slots + (size_t)(nsym & 1) * NWARPS * 3 * TJ;

@@ -58,10 +58,10 @@ def test_sym_ragged_sizes(n):
 
 
 def test_sym_too_small_falls_back_to_one_sided_kernel():
-    c = ic.random_sphere(1000, 5)
+    c = ic.random_sphere(700, 5)
     F, used, _ = engine_forces(c, True)
     assert not used  # fewer than two i-blocks: the engine keeps the one-sided CUDA kernel
-    Fo = pyport.forces(c.g, c.x, 0, 999)
+    Fo = pyport.forces(c.g, c.x, 0, 699)
     assert rel_err(F, Fo).max() < TOL64
 
 

@@ -375,6 +375,8 @@ constexpr SymVariant SYM_VARIANTS[] = {
     {6, 256, 1, 1},  // 4: one 256-thread CTA per SM; i-block 1536
     {4, 128, 3, 1},  // 5: 12 warps/SM, <= 170 registers; i-block 512
     {6, 128, 2, 4},  // 6: visiting steps unrolled by 4
+    {7, 128, 2, 2},  // 7
+    {8, 128, 2, 2},  // 8
 };
 constexpr int N_SYM_VARIANTS = sizeof(SYM_VARIANTS) / sizeof(SYM_VARIANTS[0]);
 int sym_variant() {
@@ -724,7 +726,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     sa.gpart = e->d_gpart;
     sa.n_pad = e->n_pad;
     const size_t smem = (size_t)F64_STAGES * (F64_TJ * sizeof(JRec64) + sizeof(TileInfo64)) + (size_t)(sv.threads / 32) * sizeof(WarpBounds64) +
-                        (size_t)2 * (sv.threads / 32) * 3 * F64_TJ * sizeof(double) + (size_t)4 * F64_TJ * sizeof(double) +
+                        (size_t)2 * (sv.threads / 32) * 3 * F64_TJ * sizeof(double) + (size_t)8 * F64_TJ * sizeof(double) +
                         2 * F64_STAGES * sizeof(uint64_t);
     CU_TRY(cudaEventRecord(e->ev[4], e->stream));
     for (int b0 = 0; b0 < pl.n_ib; b0 += rows) {
@@ -738,7 +740,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
         kern<<<nb * pl.n_chunks, SYM_VARIANTS[K].threads, smem, e->stream>>>(sa);                                      \
     } break;
-        switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) LAUNCH_SYM(3) LAUNCH_SYM(4) LAUNCH_SYM(5) LAUNCH_SYM(6) }
+        switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) LAUNCH_SYM(3) LAUNCH_SYM(4) LAUNCH_SYM(5) LAUNCH_SYM(6) LAUNCH_SYM(7) LAUNCH_SYM(8) }
 #undef LAUNCH_SYM
         e->launches++;
         CU_TRY(cudaGetLastError());

@@ -84,15 +84,18 @@ __device__ __forceinline__ void sym_tile(const JRec64 *__restrict__ T, const dou
     for (int g0 = 0; g0 < TJ; g0 += 32) {
         double vx = 0.0, vy = 0.0, vz = 0.0;
         const JRec64 *__restrict__ G = T + g0;
-        // per-lane records come from the SoA copy of the tile (x | y | z | m, TJ doubles each): 32 lanes read 32
-        // consecutive doubles, conflict-free, where the 64-byte AoS records would collide 16-way
-        const double *__restrict__ S = soa + g0;
-        double nx = S[lane], ny = S[TJ + lane], nz = S[2 * TJ + lane], nm = S[3 * TJ + lane];
+        // per-lane records come from the staged copy of the tile: (x,y) pairs and (z,m) pairs as 16-byte elements, each group
+        // of 32 records stored TWICE in a row of 64, so that lane l finds record (l+s) mod 32 at element l+s -- no wrap, no
+        // index arithmetic (immediate offsets once the step loop is unrolled) and conflict-free 128-bit loads, where the
+        // 64-byte AoS records would collide 16-way
+        const double2 *__restrict__ SXY = reinterpret_cast<const double2 *>(soa) + (g0 * 2) + lane;
+        const double2 *__restrict__ SZM = SXY + 2 * TJ;
+        double2 nxy = SXY[0], nzm = SZM[0];
 #pragma unroll UNR
         for (int s2 = 0; s2 < 32; ++s2) {
-            const double2 xy = make_double2(nx, ny), zm = make_double2(nz, nm);
-            const int jn = (lane + s2 + 1) & 31;  // record of the next step (prefetched)
-            nx = S[jn]; ny = S[TJ + jn]; nz = S[2 * TJ + jn]; nm = S[3 * TJ + jn];
+            const double2 xy = nxy, zm = nzm;
+            nxy = SXY[s2 + 1];  // record of the next step (prefetched)
+            nzm = SZM[s2 + 1];
             int ymin = 0x7fffffff;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -156,8 +159,8 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_sym_kernel(const S
     TileInfo64 *tinfo_s = reinterpret_cast<TileInfo64 *>(smem_raw + (size_t)STAGES * TJ * sizeof(JRec64));
     WarpBounds64 *wb_s = reinterpret_cast<WarpBounds64 *>(tinfo_s + STAGES);
     double *slots = reinterpret_cast<double *>(wb_s + NWARPS);  // [2][NWARPS][3][TJ]
-    double *soa = slots + 2 * NWARPS * 3 * TJ;                   // [4][TJ]: x | y | z | m of the current symmetric tile
-    uint64_t *full = reinterpret_cast<uint64_t *>(soa + 4 * TJ);
+    double *soa = slots + 2 * NWARPS * 3 * TJ;  // double2 [2][TJ/32][64]: (x,y) and (z,m) of the current symmetric tile, see sym_tile
+    uint64_t *full = reinterpret_cast<uint64_t *>(soa + 8 * TJ);
     uint64_t *empty = full + STAGES;
 
     const int tid = threadIdx.x;
@@ -218,11 +221,11 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_sym_kernel(const S
         }
     }
 
+    // (the softening length of the i-particles is needed in near tiles only: re-read from the record there, no registers)
     double xi[R], yi[R], zi[R], mi[R], ax[R], ay[R], az[R];
-    float si_up[R];
     {
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, rlo = 1e300, rhi = 0.0;
-        float smx = 0.f;
+        double smx = 0.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int il0 = ib * IB + r * THREADS + tid;
@@ -230,14 +233,13 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_sym_kernel(const S
             const JRec64 me = jrec[a.id_min + il];
             xi[r] = me.x; yi[r] = me.y; zi[r] = me.z;
             mi[r] = il0 < a.n_i ? me.m : 0.0;  // a clamped duplicate must not act on the j side
-            si_up[r] = __double2float_ru(me.s);
             ax[r] = ay[r] = az[r] = 0.0;
             lo[0] = fmin(lo[0], me.x); hi[0] = fmax(hi[0], me.x);
             lo[1] = fmin(lo[1], me.y); hi[1] = fmax(hi[1], me.y);
             lo[2] = fmin(lo[2], me.z); hi[2] = fmax(hi[2], me.z);
             const double rr = sqrt(me.x * me.x + me.y * me.y + me.z * me.z);
             rlo = fmin(rlo, rr); rhi = fmax(rhi, rr);
-            smx = fmaxf(smx, si_up[r]);
+            smx = fmax(smx, me.s);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -248,13 +250,13 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_sym_kernel(const S
             }
             rlo = fmin(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
             rhi = fmax(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
-            smx = fmaxf(smx, __shfl_xor_sync(0xffffffffu, smx, o));
+            smx = fmax(smx, __shfl_xor_sync(0xffffffffu, smx, o));
         }
         if (lane == 0) {
             WarpBounds64 &wb = wb_s[warp];
             wb.lo[0] = lo[0]; wb.lo[1] = lo[1]; wb.lo[2] = lo[2];
             wb.hi[0] = hi[0]; wb.hi[1] = hi[1]; wb.hi[2] = hi[2];
-            wb.rlo = rlo; wb.rhi = rhi; wb.smax = (double)smx; wb.pad = 0.0;
+            wb.rlo = rlo; wb.rhi = rhi; wb.smax = smx; wb.pad = 0.0;
         }
         __syncwarp();
     }
@@ -292,9 +294,16 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_sym_kernel(const S
             }
             int thr[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const double b = (double)si_up[r] + smax;
-                thr[r] = far ? -1 : __double2hiint(b * b) + 1;  // far tiles: nothing is ever flagged
+            for (int r = 0; r < R; ++r) thr[r] = -1;  // far tiles: nothing is ever flagged
+            if (!far) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    int il = ib * IB + r * THREADS + tid;
+                    il = il < a.n_i ? il : a.n_i - 1;
+                    const double b = jrec[a.id_min + il].s + smax;
+                    // conservative: r2 < b*b  =>  hi(r2) <= hi(b*b); one extra ulp of the high word for the rounding of b*b
+                    thr[r] = __double2hiint(b * b) + 1;
+                }
             }
             if (cls == 1) {
                 // ---- the i-block's own tiles: one-sided evaluation, checked loop (pair_r3.cuh near branch) ----
@@ -326,15 +335,15 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_sym_kernel(const S
             } else {
                 // ---- symmetric tile: systolic visit of 32 records per group ----
                 double *__restrict__ slot = slots + ((size_t)(nsym & 1) * NWARPS + warp) * 3 * TJ;
-                // AoS -> SoA copy of the tile's hot fields.  Every warp left the previous symmetric tile's loop before the
+                // staged copy of the tile's hot fields (layout: sym_tile).  Every warp left the previous symmetric tile's loop before the
                 // __syncthreads that preceded its row combine, so the buffer is free to overwrite here.
                 if (tid < TJ) {
                     const double2 xy = *reinterpret_cast<const double2 *>(&T[tid].x);
                     const double2 zm = *reinterpret_cast<const double2 *>(&T[tid].z);
-                    soa[tid] = xy.x;
-                    soa[TJ + tid] = xy.y;
-                    soa[2 * TJ + tid] = zm.x;
-                    soa[3 * TJ + tid] = zm.y;
+                    double2 *__restrict__ sxy = reinterpret_cast<double2 *>(soa) + (tid >> 5) * 64 + (tid & 31);
+                    double2 *__restrict__ szm = sxy + 2 * TJ;
+                    sxy[0] = xy; sxy[32] = xy;
+                    szm[0] = zm; szm[32] = zm;
                 }
                 __syncthreads();
                 if (far)

@@ -111,6 +111,24 @@ SYMBOLS = {
 _lib = None
 
 
+def _point_at_bundled_nccl() -> None:
+    """A Python process that may `import torch` later must not load an older system libnccl.so.2 first (one object per
+    soname): tell the library where the NCCL that PyTorch bundles lives, without importing torch (engine.cu: nccl_load)."""
+    if os.environ.get("STEPS_B200_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["STEPS_B200_NCCL_LIB"] = cand
+                return
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def load() -> C.CDLL:
     """dlopen the in-tree library; fail loudly when it has not been built."""
     global _lib
@@ -121,6 +139,7 @@ def load() -> C.CDLL:
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  steps_b200 has no fallback path."
         )
+    _point_at_bundled_nccl()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree

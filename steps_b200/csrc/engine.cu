@@ -63,10 +63,17 @@ NcclApi g_nccl;
 
 int nccl_load() {
     if (g_nccl.lib) return 0;
+    // Order matters inside a host program that brings its own NCCL (PyTorch bundles one): the dynamic loader keeps ONE
+    // object per soname, so loading an older system libnccl.so.2 first would later break `import torch`.  Hence:
+    // (1) an explicit path (STEPS_B200_NCCL_LIB; steps_b200/_lib.py points it at the bundled library when there is one),
+    // (2) whatever libnccl.so.2 the process has already loaded, (3) the system library.
+    if (const char *path = getenv("STEPS_B200_NCCL_LIB"))
+        if (*path) g_nccl.lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl.lib) g_nccl.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char *n : names) {
-        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (g_nccl.lib) break;
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
     }
     if (!g_nccl.lib) return fail(std::string("cannot dlopen libnccl.so.2: ") + dlerror());
 #define LOADSYM(field, name)                                                      \

@@ -34,4 +34,7 @@ stamp "ncu --set full, one launch of the sym kernel at N=400k"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:force_r3_f64_sym -s 1 -c 1 -o $O/${TAG}_sym_n400k \
     python bench.py --steps 1 --warmup 1 --n 400000 --no-cpu > $O/${TAG}_ncu_full.out 2>&1
 tail -2 $O/${TAG}_ncu_full.out | cut -c1-300
+stamp "other configurations (C1 shape, FP32, S^1xR^2, T^3): pair-kernel throughput"
+timeout 300 python tools/topo_bench.py c1,r3f32:2000000,s1r2nl:400000,s1r2:200000,t3:64 > $O/${TAG}_topo_bench.txt 2> $O/${TAG}_topo_bench.err
+cut -c1-330 $O/${TAG}_topo_bench.txt; tail -2 $O/${TAG}_topo_bench.err
 stamp "done"

@@ -118,31 +118,13 @@ namespace {
 // Variant 0 is the production shape; the others exist for on-device tuning (STEPS_B200_F64_VARIANT=k).
 constexpr int F64_TJ = 128, F64_STAGES = 3;
 struct F64Variant {
-    int R, threads, minb, unroll, experiment;
+    int R, threads, minb, unroll;
 };
 constexpr F64Variant F64_VARIANTS[] = {
     {8, 128, 2, 1},  // 0: PRODUCTION.  255 regs, 8 warps/SM
     {4, 256, 2, 2},  // 1: 128 regs, 16 warps/SM
-    {4, 128, 4, 4},  // 2
-    {4, 128, 5, 2},  // 3: <=102 regs, 20 warps/SM
-    {2, 128, 8, 4},  // 4: <=64 regs, 32 warps/SM
-    {3, 128, 6, 2},  // 5: <=85 regs, 24 warps/SM
-    {4, 128, 4, 2},  // 6
-    {8, 128, 2, 2},  // 7
-    {6, 128, 3, 2},  // 8: <=170 regs, 12 warps/SM
-    {6, 128, 3, 1},  // 9
-    {8, 64, 4, 1},   // 10: 255 regs, 8 warps/SM in 64-thread CTAs
-    {5, 128, 3, 2},  // 11
-    {8, 128, 2, 1, 1},  // 12: TIMING EXPERIMENT: every tile takes the far loop (wrong forces for r < beta)
-    {8, 128, 2, 1, 2},  // 13: TIMING EXPERIMENT: every tile takes the checked loop (correct, slower)
-    {4, 256, 2, 2, 1},  // 14: TIMING EXPERIMENT (far only)
-    {4, 256, 2, 2, 2},  // 15: TIMING EXPERIMENT (checked only)
-    {10, 128, 2, 1},    // 16
-    {12, 128, 2, 1},    // 17
-    {12, 64, 4, 1},     // 18
-    {10, 64, 4, 1},     // 19
-    {8, 128, 1, 1},     // 20: ONE warp per SMSP (dynamic smem padded so that a single CTA fits per SM): no warp switching
-    {8, 128, 1, 2},     // 21: same, j unrolled by 2
+    {8, 128, 2, 2},  // 2: j unrolled by 2
+    {6, 128, 3, 2},  // 3: <=170 regs, 12 warps/SM
 };
 constexpr int N_F64_VARIANTS = sizeof(F64_VARIANTS) / sizeof(F64_VARIANTS[0]);
 int f64_variant() {
@@ -159,14 +141,10 @@ struct F32Variant {
     int R, threads, minb, unroll;
 };
 constexpr F32Variant F32_VARIANTS[] = {
-    {8, 256, 2, 2},   // 0: <=128 regs, 16 warps/SM
+    {8, 256, 2, 2},   // 0: PRODUCTION.  <=128 regs, 16 warps/SM
     {16, 128, 2, 1},  // 1: <=255 regs, 8 warps/SM
-    {16, 128, 3, 1},  // 2: <=170 regs, 12 warps/SM
-    {8, 128, 4, 2},   // 3
-    {8, 128, 5, 2},   // 4: <=102 regs, 20 warps/SM
-    {12, 128, 3, 1},  // 5
-    {4, 256, 4, 4},   // 6: <=64 regs, 32 warps/SM
-    {8, 128, 4, 4},   // 7
+    {8, 128, 4, 2},   // 2
+    {12, 128, 3, 1},  // 3
 };
 constexpr int N_F32_VARIANTS = sizeof(F32_VARIANTS) / sizeof(F32_VARIANTS[0]);
 int f32_variant() {
@@ -347,20 +325,17 @@ struct S1R2Variant {
     int R, threads, minb;
 };
 constexpr S1R2Variant S1R2_VARIANTS[] = {
-    {4, 128, 4},  // 0: 128 regs, 16 warps/SM
-    {2, 128, 8},  // 1: 64 regs, 32 warps/SM
-    {6, 128, 2},  // 2: 255 regs, 8 warps/SM
-    {3, 128, 5},  // 3: PRODUCTION.  102 regs, 20 warps/SM
-    {4, 256, 2},  // 4: 128 regs, 16 warps/SM in 256-thread CTAs
-    {8, 128, 2},  // 5: 255 regs
+    {3, 128, 5},  // 0: PRODUCTION (fastest of the sweep recorded in git history, 2.1e11 pairs/s at N=200k).  102 regs, 20 warps/SM
+    {4, 128, 4},  // 1: 128 regs, 16 warps/SM
+    {2, 128, 8},  // 2: 64 regs, 32 warps/SM
 };
 constexpr int N_S1R2_VARIANTS = sizeof(S1R2_VARIANTS) / sizeof(S1R2_VARIANTS[0]);
 int s1r2_variant() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("STEPS_B200_S1R2_VARIANT");
-        v = s ? atoi(s) : 3;  // production shape: fastest of the sweep in profiles/ (R=3, 20 warps/SM)
-        if (v < 0 || v >= N_S1R2_VARIANTS) v = 3;
+        v = s ? atoi(s) : 0;
+        if (v < 0 || v >= N_S1R2_VARIANTS) v = 0;
     }
     return v;
 }
@@ -375,23 +350,18 @@ struct SymVariant {
     int R, threads, minb, unroll;
 };
 constexpr SymVariant SYM_VARIANTS[] = {
-    {6, 128, 2, 1},  // 0: 248 registers, no spills; i-block 768
-    {8, 128, 2, 1},  // 1: 255 registers, a few spills outside the hot loop; i-block 1024
-    {7, 128, 2, 1},  // 2: i-block 896
-    {6, 128, 2, 2},  // 3: PRODUCTION (fastest of the sweeps in profiles/): visiting steps unrolled by 2, 250 registers, no spills
-    {6, 256, 1, 1},  // 4: one 256-thread CTA per SM; i-block 1536
-    {4, 128, 3, 1},  // 5: 12 warps/SM, <= 170 registers; i-block 512
-    {6, 128, 2, 4},  // 6: visiting steps unrolled by 4
-    {7, 128, 2, 2},  // 7
-    {8, 128, 2, 2},  // 8
+    {6, 128, 2, 2},  // 0: PRODUCTION (fastest of the sweeps in profiles/r1u_*): i-block 768, visiting steps unrolled by 2, 250 registers, no spills
+    {6, 128, 2, 1},  // 1: not unrolled
+    {7, 128, 2, 2},  // 2: i-block 896 (a few spills outside the hot loop)
+    {8, 128, 2, 2},  // 3: i-block 1024 (spills outside the hot loop)
 };
 constexpr int N_SYM_VARIANTS = sizeof(SYM_VARIANTS) / sizeof(SYM_VARIANTS[0]);
 int sym_variant() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("STEPS_B200_SYM_VARIANT");
-        v = s ? atoi(s) : 3;
-        if (v < 0 || v >= N_SYM_VARIANTS) v = 3;
+        v = s ? atoi(s) : 0;
+        if (v < 0 || v >= N_SYM_VARIANTS) v = 0;
     }
     return v;
 }
@@ -584,18 +554,15 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     if (tuned_f64) {
         size_t smem = (size_t)F64_STAGES * (F64_TJ * sizeof(JRec64) + sizeof(TileInfo64)) + (size_t)(fv.threads / 32) * sizeof(WarpBounds64) +
                       2 * F64_STAGES * sizeof(uint64_t);
-        if (fv.minb == 1) smem = std::max(smem, (size_t)120 * 1024);  // occupancy limiter of the one-warp-per-SMSP shapes
 #define LAUNCH_F64(K)                                                                                                       \
     case K: {                                                                                                               \
         auto kern = force_r3_f64_kernel<F64_VARIANTS[K].R, F64_VARIANTS[K].threads, F64_TJ, F64_STAGES, F64_VARIANTS[K].minb, \
-                                        F64_VARIANTS[K].unroll, F64_VARIANTS[K].experiment>;                                                            \
+                                        F64_VARIANTS[K].unroll>;                                                            \
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
         kern<<<pl.ctas, F64_VARIANTS[K].threads, smem, e->stream>>>(a);                                                     \
     } break;
         switch (f64_variant()) {
-            LAUNCH_F64(0) LAUNCH_F64(1) LAUNCH_F64(2) LAUNCH_F64(3) LAUNCH_F64(4) LAUNCH_F64(5) LAUNCH_F64(6) LAUNCH_F64(7)
-            LAUNCH_F64(8) LAUNCH_F64(9) LAUNCH_F64(10) LAUNCH_F64(11) LAUNCH_F64(12) LAUNCH_F64(13) LAUNCH_F64(14) LAUNCH_F64(15)
-            LAUNCH_F64(16) LAUNCH_F64(17) LAUNCH_F64(18) LAUNCH_F64(19) LAUNCH_F64(20) LAUNCH_F64(21)
+            LAUNCH_F64(0) LAUNCH_F64(1) LAUNCH_F64(2) LAUNCH_F64(3)
         }
 #undef LAUNCH_F64
     } else if (tuned_f32) {
@@ -609,7 +576,7 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         kern<<<pl.ctas, F32_VARIANTS[K].threads, smem, e->stream>>>(a);                                                     \
     } break;
         switch (f32_variant()) {
-            LAUNCH_F32(0) LAUNCH_F32(1) LAUNCH_F32(2) LAUNCH_F32(3) LAUNCH_F32(4) LAUNCH_F32(5) LAUNCH_F32(6) LAUNCH_F32(7)
+            LAUNCH_F32(0) LAUNCH_F32(1) LAUNCH_F32(2) LAUNCH_F32(3)
         }
 #undef LAUNCH_F32
     } else if (sizeof(T) == 8 && tuned_s1r2(e)) {
@@ -646,7 +613,7 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         else LAUNCH_S1R2_VM(V, 5)                                          \
         break;
         switch (s1r2_variant()) {
-            LAUNCH_S1R2_V(0) LAUNCH_S1R2_V(1) LAUNCH_S1R2_V(2) LAUNCH_S1R2_V(3) LAUNCH_S1R2_V(4) LAUNCH_S1R2_V(5)
+            LAUNCH_S1R2_V(0) LAUNCH_S1R2_V(1) LAUNCH_S1R2_V(2)
         }
 #undef LAUNCH_S1R2_V
 #undef LAUNCH_S1R2_VM
@@ -747,7 +714,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
         kern<<<nb * pl.n_chunks, SYM_VARIANTS[K].threads, smem, e->stream>>>(sa);                                      \
     } break;
-        switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) LAUNCH_SYM(3) LAUNCH_SYM(4) LAUNCH_SYM(5) LAUNCH_SYM(6) LAUNCH_SYM(7) LAUNCH_SYM(8) }
+        switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) LAUNCH_SYM(3) }
 #undef LAUNCH_SYM
         e->launches++;
         CU_TRY(cudaGetLastError());

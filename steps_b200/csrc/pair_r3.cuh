@@ -144,7 +144,7 @@ struct __align__(16) WarpBounds64 {
         az[r] = fma(w, dz, az[r]);                                                                \
     }
 
-template <int R, int THREADS, int TJ, int STAGES, int MINB, int UNROLL, int EXPERIMENT = 0>
+template <int R, int THREADS, int TJ, int STAGES, int MINB, int UNROLL>
 __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_kernel(const R3LaunchArgs a) {
     constexpr int NWARPS = THREADS / 32;
     constexpr int JB = 16;  // sub-block between slow-path checks (near tiles)
@@ -256,8 +256,6 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_kernel(const R3Lau
             const double b = (wb->smax + smax) * 1.000001;
             far = (gap2 > b * b) || (rg > b);
         }
-        if (EXPERIMENT == 1) far = true;   // timing experiment only
-        if (EXPERIMENT == 2) far = false;  // timing experiment only
         if (far) {
 #pragma unroll UNROLL
             for (int jj = 0; jj < TJ; ++jj) {

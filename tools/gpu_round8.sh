@@ -20,7 +20,7 @@ timeout 420 python bench.py --steps 3 --warmup 3 > $O/${TAG}_bench_c2_1gpu.json 
 cat $O/${TAG}_bench_c2_1gpu.json | cut -c1-1800; tail -3 $O/${TAG}_bench_c2_1gpu.err
 
 stamp "sweep N=400k: sym variants and chunk counts"
-( for v in 0 1 2 3 4 5 6; do SWEEP_SYM=1 STEPS_B200_SYM_VARIANT=$v python tools/sweep_f64.py 400000 0; done
+( for v in 0 1 2 3; do SWEEP_SYM=1 STEPS_B200_SYM_VARIANT=$v python tools/sweep_f64.py 400000 0; done
   for c in 28 112 224; do echo "chunks=$c"; STEPS_B200_SYM_CHUNKS=$c SWEEP_SYM=1 python tools/sweep_f64.py 400000 0; done ) > $O/${TAG}_sym_sweep_n400k.txt 2>&1
 cut -c1-330 $O/${TAG}_sym_sweep_n400k.txt
 

@@ -274,6 +274,38 @@ def test_s1r2nl_z_outside_box_takes_exact_kernel():
     assert np.percentile(e, 99) < TOL64 and e.max() < 50 * TOL64
 
 
+def test_t3_outside_box_takes_exact_kernel_and_large_softening():
+    """T^3: (a) positions a caller did not wrap into [0, L) must not reach the tuned kernel's |d| < L shortcut (device gate ->
+    exact-branch kernel), (b) back inside the box, (c) softening lengths large enough that many pairs take the softened branches"""
+    if not pyref.available("t3_f64"):
+        pytest.skip("T^3 table needs oracle/_ref")
+    c = ic.t3_lattice(12, 71, L=30.0, is_periodic=2)
+    g = c.g
+    r = pyref.Reference("t3_f64")
+    r.configure(g, 400)
+    r.build_tables()
+    r.export_tables(g)
+    x = c.x.reshape(-1, 3).copy()
+    x[::5, 0] += 30.0
+    x[2::7, 2] -= 30.0
+    xs = np.ascontiguousarray(x.reshape(-1))
+    for xx in (xs, c.x):
+        Fo = r.forces(xx, 0, g.N - 1, 0)
+        F = gpu_forces(g, xx, 0, g.N - 1)
+        e = rel_err(F, Fo)
+        assert np.percentile(e, 99) < TOL64 and e.max() < 50 * TOL64
+    g.ParticleRadi = 0.8 * 30.0 / 12  # beta = 1.6 lattice spacings: nearest neighbours are softened
+    sb.calculate_softening_length(g)
+    r.configure(g, 400)  # the reference derives the same lengths from ParticleRadi (utils.cc:59-82)
+    r.build_tables()
+    assert np.allclose(r.softening(), g.SOFT_LENGTH, rtol=1e-14)
+    Fo = r.forces(c.x, 0, g.N - 1, 0)
+    F = gpu_forces(g, c.x, 0, g.N - 1)
+    e = rel_err(F, Fo)
+    print(f"t3 softened: |dF|/|F| p99 {np.percentile(e, 99):.2e} max {e.max():.2e}")
+    assert np.percentile(e, 99) < TOL64 and e.max() < 50 * TOL64
+
+
 def test_full_size_c2_properties():
     """BASELINE.json configs[1]: N = 2,000,000 FP64 compactified R^3 (size-independent properties + sampled oracle rows)"""
     c = ic.config_c2()

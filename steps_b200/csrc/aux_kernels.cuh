@@ -5,7 +5,6 @@
 #include "pair_r3_f32.cuh"
 #include "pair_s1r2.cuh"
 #include "pair_r3_sym.cuh"
-#include "pair_t3.cuh"
 
 namespace steps {
 
@@ -29,17 +28,13 @@ __global__ void tile_smax_kernel(const T *__restrict__ s, int n, int tj, int n_t
 template <int TJ_>
 __global__ void __launch_bounds__(TJ_) pack_kernel_f64(const double *__restrict__ x, const double *__restrict__ m, const double *__restrict__ s,
                                                         const double *__restrict__ smax_tile, JRec64 *__restrict__ out,
-                                                        TileInfo64 *__restrict__ tinfo, int n, double zbox, int *__restrict__ z_outside, int planar,
-                                                        int box_first_axis) {
+                                                        TileInfo64 *__restrict__ tinfo, int n, double zbox, int *__restrict__ z_outside, int planar) {
     const int t = blockIdx.x;
     const int j = t * TJ_ + threadIdx.x;
-    // periodic topologies: note any periodic coordinate outside [0, L) (S^1xR^2: z only, box_first_axis = 2; T^3: all three,
-    // box_first_axis = 0).  The tuned kernels assume |d| < L along periodic axes (pair_s1r2.cuh, pair_t3.cuh).
+    // S^1xR^2: note any z outside [0, L) (the tuned image-sum kernel assumes |dz| < L, pair_s1r2.cuh)
     if (z_outside && j < n) {
-        for (int k = box_first_axis; k < 3; ++k) {
-            const double zz = x[3 * (size_t)j + k];
-            if (!(zz >= 0.0 && zz < zbox)) atomicOr(z_outside, 1);
-        }
+        const double zz = x[3 * (size_t)j + 2];
+        if (!(zz >= 0.0 && zz < zbox)) atomicOr(z_outside, 1);
     }
     JRec64 r;
     const double sm = smax_tile[t];

@@ -210,9 +210,7 @@ struct steps_b200_engine {
     cudaStream_t stream = nullptr;
     void *d_x = nullptr, *d_v = nullptr, *d_F = nullptr, *d_m = nullptr, *d_s = nullptr;
     void *d_tinfo = nullptr;
-    int *d_zflag = nullptr;  // periodic topologies: set by the pack kernel when some periodic coordinate lies outside [0, L)
-    double4 *d_table_pad = nullptr;  // T^3: halo-padded 32-byte-cell copy of the Ewald table (pair_t3.cuh)
-    size_t table_pad_cells = 0;
+    int *d_zflag = nullptr;  // S^1xR^2: set by the pack kernel when some z lies outside [0, L)
     void *d_jrec = nullptr, *d_smax = nullptr, *d_fpart = nullptr, *d_table = nullptr, *d_radial = nullptr;
     double *d_errmax = nullptr, *h_errmax = nullptr;
     size_t fpart_bytes = 0;
@@ -307,21 +305,6 @@ int upload_tables(steps_b200_engine *e) {
             e->table_bytes = bytes;
         }
         CU_TRY(cudaMemcpyAsync(e->d_table, p.ewald_table, bytes, cudaMemcpyHostToDevice, e->stream));
-        if (p.topology == STEPS_TOPO_T3 && e->real_bytes == 8) {
-            // halo-padded 32-byte-cell copy for the tuned T^3 kernel (pair_t3.cuh)
-            const int P = p.table_dim0 + 4;
-            const size_t cells = (size_t)P * P * P;
-            if (cells != e->table_pad_cells) {
-                if (e->d_table_pad) CU_TRY(cudaFree(e->d_table_pad));
-                e->d_table_pad = nullptr;
-                CU_TRY(cudaMalloc(&e->d_table_pad, cells * sizeof(double4)));
-                e->table_pad_cells = cells;
-            }
-            t3_pad_table_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>(static_cast<const double *>(e->d_table), p.table_dim0, P,
-                                                                                         e->d_table_pad);
-            e->launches++;
-            CU_TRY(cudaGetLastError());
-        }
     }
     if (p.radial_table && p.radial_table_size > 0) {
         const size_t bytes = (size_t)p.radial_table_size * e->real_bytes;
@@ -520,46 +503,12 @@ Plan sym_plan(const steps_b200_engine *e, int n_i) {
     return p;
 }
 
-
-// the tuned T^3 kernel of pair_t3.cuh: FP64 build with the Ewald lookup table (IS_PERIODIC >= 2)
-struct T3Variant {
-    int R, threads, minb;
-};
-constexpr T3Variant T3_VARIANTS[] = {
-    {2, 128, 4},  // 0: 128 regs, 16 warps/SM
-    {2, 128, 3},  // 1: 168 regs, 12 warps/SM
-    {1, 128, 4},  // 2
-    {4, 128, 2},  // 3: 255 regs, 8 warps/SM
-};
-constexpr int N_T3_VARIANTS = sizeof(T3_VARIANTS) / sizeof(T3_VARIANTS[0]);
-int t3_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char *s = getenv("STEPS_B200_T3_VARIANT");
-        v = s ? atoi(s) : 0;
-        if (v < 0 || v >= N_T3_VARIANTS) v = 0;
-    }
-    return v;
-}
-bool tuned_t3(const steps_b200_engine *e) {
-    static const int on = [] {
-        const char *s = getenv("STEPS_B200_T3_TUNED");  // default off until verified on the GPU
-        return (s && atoi(s) != 0) ? 1 : 0;
-    }();
-    return on && e->real_bytes == 8 && e->p.topology == STEPS_TOPO_T3 && e->p.is_periodic >= 2 && e->d_table_pad != nullptr;
-}
-
 Plan plan_for(const steps_b200_engine *e, int n_i) {
     int ib = GEN_R * GEN_THREADS, per_sm = 4;
     if (tuned_s1r2(e)) {
         const S1R2Variant sv = S1R2_VARIANTS[s1r2_variant()];
         ib = sv.R * sv.threads;
         per_sm = sv.minb;
-    }
-    if (tuned_t3(e)) {
-        const T3Variant tv = T3_VARIANTS[t3_variant()];
-        ib = tv.R * tv.threads;
-        per_sm = tv.minb;
     }
     if (e->p.topology == STEPS_TOPO_R3) {
         if (e->real_bytes == 8) {
@@ -630,34 +579,6 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
             LAUNCH_F32(0) LAUNCH_F32(1) LAUNCH_F32(2) LAUNCH_F32(3)
         }
 #undef LAUNCH_F32
-    } else if (sizeof(T) == 8 && tuned_t3(e)) {
-        // tuned kernel when every coordinate is inside [0, L) (device flag written by the pack kernel), else the exact-branch
-        // kernel in the same launch shape: both are launched, exactly one of them does the work
-        const size_t smem = (size_t)GEN_STAGES * GEN_TJ * sizeof(JRec64) + 2 * GEN_STAGES * sizeof(uint64_t);
-        T3Consts k{};
-        k.L = e->tp.L;
-        k.halfL = 0.5 * e->tp.L;
-        k.h = e->tp.L / (double)e->tp.dim0;  // grid_spacing = L / Ngrid (forces_cuda.cu:90)
-        k.inv_h = 1.0 / k.h;
-        k.ngrid = e->tp.dim0;
-        k.P = e->tp.dim0 + 4;
-        k.tab = e->d_table_pad;
-#define LAUNCH_T3(V)                                                                                                          \
-    case V: {                                                                                                                 \
-        a.gate = e->d_zflag;                                                                                                  \
-        a.gate_value = 0;                                                                                                     \
-        auto kern = force_t3_f64_kernel<T3_VARIANTS[V].R, T3_VARIANTS[V].threads, GEN_TJ, GEN_STAGES, T3_VARIANTS[V].minb>;    \
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                           \
-        kern<<<pl.ctas, T3_VARIANTS[V].threads, smem, e->stream>>>(a, k);                                                     \
-        e->launches++;                                                                                                        \
-        CU_TRY(cudaGetLastError());                                                                                           \
-        a.gate_value = 1;                                                                                                     \
-        auto gen = force_generic_kernel<double, 1, T3_VARIANTS[V].R, T3_VARIANTS[V].threads, GEN_TJ, GEN_STAGES>;             \
-        CU_TRY(cudaFuncSetAttribute(gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                            \
-        gen<<<pl.ctas, T3_VARIANTS[V].threads, smem, e->stream>>>(a, e->tp);                                                  \
-    } break;
-        switch (t3_variant()) { LAUNCH_T3(0) LAUNCH_T3(1) LAUNCH_T3(2) LAUNCH_T3(3) }
-#undef LAUNCH_T3
     } else if (sizeof(T) == 8 && tuned_s1r2(e)) {
         // tuned image-sum kernel when every z is inside [0, L) (device flag written by the pack kernel), else the exact-branch
         // kernel in the same launch shape: both are launched, exactly one of them does the work
@@ -812,13 +733,13 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
 int pack(steps_b200_engine *e) {
     if (e->real_bytes == 8) {
         int *zflag = nullptr;
-        if (tuned_s1r2(e) || tuned_t3(e)) {
+        if (tuned_s1r2(e)) {
             zflag = e->d_zflag;
             CU_TRY(cudaMemsetAsync(zflag, 0, sizeof(int), e->stream));
         }
         pack_kernel_f64<TJ><<<e->n_tiles, TJ, 0, e->stream>>>((const double *)e->d_x, (const double *)e->d_m, (const double *)e->d_s,
                                                               (const double *)e->d_smax, (JRec64 *)e->d_jrec, (TileInfo64 *)e->d_tinfo, e->n,
-                                                              e->p.L, zflag, tuned_s1r2(e) ? 1 : 0, tuned_t3(e) ? 0 : 2);
+                                                              e->p.L, zflag, zflag != nullptr);
     }
     else
         pack_kernel_f32<TJ><<<e->n_tiles, TJ, 0, e->stream>>>((const float *)e->d_x, (const float *)e->d_m, (const float *)e->d_s,
@@ -963,7 +884,7 @@ extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym, e->d_table_pad};
+    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (e->h_errmax) cudaFreeHost(e->h_errmax);

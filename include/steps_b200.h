@@ -95,6 +95,18 @@ int steps_b200_softening_f32(const float *M, int n, float particle_radii, float 
                              float *rho_part_out);
 
 /* ------------------------------------------------------------------------------------------
+ * (1b) Table producer: the T^3 Ewald force-correction lookup table on the GPU.
+ *     Replaces calculate_t3_ewald_lookup_table() + ewald_force_correction() + ewald_space()
+ *     (ewald_space.cc:288-383, :198-286, :118-196) as called at main.cc:467-494.  table_host: [ngrid^3][3] doubles,
+ *     layout of ewald_space.cc:46-49 -- exactly what steps_b200_params.ewald_table expects.
+ *     t3_ewald_defaults restates main.cc:425-446 (IS_PERIODIC 2/3/4 -> 63/127/255 grid, cuts 2.6/3.6/4.6 L and
+ *     8/10/12, alpha = 2/L).  ewald_space_count(R) = number of lattice vectors ewald_space(R, ...) enumerates (host only).
+ * ------------------------------------------------------------------------------------------ */
+int steps_b200_t3_ewald_defaults(int is_periodic, double L, int *ngrid, double *alpha, double *rel_cut, double *rec_cut);
+int steps_b200_ewald_space_count(double R);
+int steps_b200_t3_ewald_table_f64(int ngrid, double L, double alpha, double rel_cut, double rec_cut, double *table_host, int device);
+
+/* ------------------------------------------------------------------------------------------
  * (2) Device-resident engine (north_star item 3): x, v, F, M, s stay in HBM across KDK steps.
  *     One engine per process per GPU.  Replaces step() (step.cc:100-312), calculate_init_h()
  *     (step.cc:35-98) and the per-step host<->device traffic of forces_cuda.cu:976-1105.

@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
     UNIT_T,
     UNIT_V,
     calculate_softening_length,
+    calculate_t3_ewald_lookup_table,
     fma_peak,
     fma_peak_sustained,
     force_entry,
@@ -20,4 +21,5 @@ from .api import (  # noqa: F401
     forces_periodic_z,
     friedmann_solver_step,
     partition,
+    t3_ewald_defaults,
 )

@@ -209,6 +209,25 @@ def partition(n: int, nranks: int, rank: int) -> tuple:
     return lo.value, hi.value
 
 
+def t3_ewald_defaults(is_periodic: int, L: float) -> dict:
+    """main.cc:425-446: grid size, alpha and cuts of the T^3 Ewald table for IS_PERIODIC = 2, 3, 4"""
+    ng, al, rel, rec = C.c_int(), C.c_double(), C.c_double(), C.c_double()
+    check(_lib.load().steps_b200_t3_ewald_defaults(is_periodic, L, C.byref(ng), C.byref(al), C.byref(rel), C.byref(rec)))
+    return {"ngrid": ng.value, "alpha": al.value, "rel_cut": rel.value, "rec_cut": rec.value}
+
+
+def calculate_t3_ewald_lookup_table(g: Globals, device: int = 0) -> np.ndarray:
+    """ewald_space.cc:288-383 on the GPU: builds T3_EWALD_FORCE_TABLE for g.IS_PERIODIC / g.L (setup of main.cc:425-494) and
+    stores it, with N_EWALD_FORCE_GRID, in g (REAL of the build).  Returns the FP64 table [Ngrid, Ngrid, Ngrid, 3]."""
+    d = t3_ewald_defaults(g.IS_PERIODIC, g.L)
+    n = d["ngrid"]
+    tab = np.empty(n * n * n * 3, dtype=np.float64)
+    check(_lib.load().steps_b200_t3_ewald_table_f64(n, g.L, d["alpha"], d["rel_cut"], d["rec_cut"], tab.ctypes.data, device))
+    g.N_EWALD_FORCE_GRID = n
+    g.T3_EWALD_FORCE_TABLE = np.ascontiguousarray(tab, dtype=g.REAL)
+    return tab.reshape(n, n, n, 3)
+
+
 def sym_rules(n: int, nranks: int, rank: int, ib_size: int):
     """host-only rule builder of the action-reaction path: -> (i_lo, i_hi, rules[nb, 16]) or None"""
     nb_max = (n + ib_size - 1) // ib_size + 1

@@ -18,6 +18,7 @@
 
 #include "../../include/steps_b200.h"
 #include "aux_kernels.cuh"
+#include "ewald_t3.cuh"
 
 using namespace steps;
 
@@ -1166,6 +1167,83 @@ extern "C" int steps_b200_engine_launch_shape(steps_b200_engine *e, int id_min, 
     out4[1] = pl.n_chunks;
     out4[2] = pl.ctas;
     out4[3] = TJ;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ table producers
+// main.cc:425-446: IS_PERIODIC -> (grid size, real-space cut in units of L, reciprocal cut); alpha = 2/L
+extern "C" int steps_b200_t3_ewald_defaults(int is_periodic, double L, int *ngrid, double *alpha, double *rel_cut, double *rec_cut) {
+    if (is_periodic < 2 || is_periodic > 4 || !(L > 0.0)) return fail("T^3 Ewald table needs IS_PERIODIC in 2..4 and L > 0");
+    const int ng[3] = {63, 127, 255};
+    const double rel[3] = {2.6, 3.6, 4.6}, rec[3] = {8.0, 10.0, 12.0};
+    if (ngrid) *ngrid = ng[is_periodic - 2];
+    if (alpha) *alpha = 2.0 / L;
+    if (rel_cut) *rel_cut = rel[is_periodic - 2];
+    if (rec_cut) *rec_cut = rec[is_periodic - 2];
+    return 0;
+}
+
+// host-only: number of lattice vectors ewald_space(R, ...) enumerates (the reference returns the last index = this - 1)
+extern "C" int steps_b200_ewald_space_count(double R) {
+    std::vector<EwaldIdx> v;
+    build_ewald_space(R, v);
+    return (int)v.size();
+}
+
+extern "C" int steps_b200_t3_ewald_table_f64(int ngrid, double L, double alpha, double rel_cut, double rec_cut, double *table_host,
+                                             int device) {
+    if (!table_host) return fail("table is NULL");
+    if (ngrid < 3 || ngrid > 1023 || (ngrid & 1) == 0) return fail("Ngrid must be odd (centre point and axes on the grid), 3..1023");
+    if (!(L > 0.0) || !(alpha > 0.0) || !(rel_cut > 0.0) || !(rec_cut > 0.0)) return fail("L, alpha, rel_cut, rec_cut must be positive");
+    int ndev = steps_b200_device_count();
+    if (ndev == 0) return fail("no CUDA device available: libstepsb200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("bad device ordinal");
+    DeviceGuard dg_;
+    CU_TRY(cudaSetDevice(device));
+    std::vector<EwaldIdx> re, rc;
+    build_ewald_space(rel_cut + 1.0, re);  // main.cc:467-468
+    build_ewald_space(rec_cut + 2.0, rc);
+    std::vector<int> pts;
+    for (int i = ngrid / 2; i < ngrid; ++i)
+        for (int j = ngrid / 2; j <= i; ++j)
+            for (int k = ngrid / 2; k <= j; ++k) {
+                pts.push_back(i);
+                pts.push_back(j);
+                pts.push_back(k);
+            }
+    const int n_points = (int)(pts.size() / 3);
+    const size_t tab_bytes = (size_t)ngrid * ngrid * ngrid * 3 * sizeof(double);
+    T3EwaldParams p{ngrid, L, alpha, rel_cut, rec_cut, (int)re.size(), (int)rc.size()};
+    int *d_pts = nullptr;
+    EwaldIdx *d_re = nullptr, *d_rc = nullptr;
+    double *d_tab = nullptr;
+    auto cleanup = [&]() {
+        if (d_pts) cudaFree(d_pts);
+        if (d_re) cudaFree(d_re);
+        if (d_rc) cudaFree(d_rc);
+        if (d_tab) cudaFree(d_tab);
+    };
+#define T_TRY(expr)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e_ = (expr);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            cleanup();                                                                                       \
+            return fail(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr);               \
+        }                                                                                                    \
+    } while (0)
+    T_TRY(cudaMalloc(&d_pts, pts.size() * sizeof(int)));
+    T_TRY(cudaMalloc(&d_re, re.size() * sizeof(EwaldIdx)));
+    T_TRY(cudaMalloc(&d_rc, rc.size() * sizeof(EwaldIdx)));
+    T_TRY(cudaMalloc(&d_tab, tab_bytes));
+    T_TRY(cudaMemcpy(d_pts, pts.data(), pts.size() * sizeof(int), cudaMemcpyHostToDevice));
+    T_TRY(cudaMemcpy(d_re, re.data(), re.size() * sizeof(EwaldIdx), cudaMemcpyHostToDevice));
+    T_TRY(cudaMemcpy(d_rc, rc.data(), rc.size() * sizeof(EwaldIdx), cudaMemcpyHostToDevice));
+    T_TRY(cudaMemset(d_tab, 0, tab_bytes));
+    t3_ewald_table_kernel<<<(n_points + 63) / 64, 64>>>(d_pts, n_points, p, d_re, d_rc, d_tab);
+    T_TRY(cudaGetLastError());
+    T_TRY(cudaMemcpy(table_host, d_tab, tab_bytes, cudaMemcpyDeviceToHost));
+#undef T_TRY
+    cleanup();
     return 0;
 }
 

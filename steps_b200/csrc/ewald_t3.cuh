@@ -1,0 +1,160 @@
+// ewald_t3.cuh -- GPU builder of the T^3 Ewald force-correction lookup table.
+//
+// Replaces calculate_t3_ewald_lookup_table() + ewald_force_correction() + ewald_space()
+// (StePS/src/ewald_space.cc:288-383, :198-286, :118-196; set up by main.cc:425-494): for every grid point of the
+// fundamental wedge i >= j >= k >= Ngrid/2 of the cell-centred Ngrid^3 grid on [-L/2, L/2)^3,
+//     D(r) = F_real(r) + F_rec(r) - F_newton(r)          (Hernquist, Bouchet & Suto 1991)
+//     F_real = - sum_n (r + nL) [erfc(a R) + 2 a R exp(-a^2 R^2)/sqrt(pi)] / R^3,   R = |r + nL| <= rel_cut L
+//     F_rec  = - sum_h k (4 pi / V) exp(-k^2 / 4 a^2) sin(k.r) / k^2,               k = 2 pi h / L, |k| <= rec_cut
+//     F_newton = - r / |r|^3
+// and the other 47 images of the point are filled by the octahedral symmetry of the cube.
+// One thread per wedge point; the two lattice sums run in the reference's index order inside the thread, so the value of
+// an entry differs from the reference's only by the last bits of erfc/exp/sin (CUDA math library vs glibc).  The images
+// are written in the reference's order (24 proper rotations, each followed by its inversion; last write wins on the
+// symmetry planes, where several images coincide).  Note the reference's convention, kept here: rec_cut is compared with
+// |k| in physical units while the index list is generated in integer units (ewald_space.cc:253-256, main.cc:468).
+#pragma once
+#include <cmath>
+#include <vector>
+#include <cuda_runtime.h>
+
+namespace steps {
+
+struct EwaldIdx {
+    int x, y, z, n2;
+};
+
+// lattice vectors with |n| < R in the reference's enumeration order (ewald_space.cc:118-196)
+inline void build_ewald_space(double R, std::vector<EwaldIdx> &out) {
+    out.clear();
+    for (int i = 0; i < R; ++i)
+        for (int j = 0; j < R; ++j)
+            for (int k = 0; k < R; ++k) {
+                const int n2 = i * i + j * j + k * k;
+                if (!((double)n2 < R * R)) continue;
+                out.push_back({i, j, k, n2});
+                if (i != 0) out.push_back({-i, j, k, n2});
+                if (j != 0) out.push_back({i, -j, k, n2});
+                if (k != 0) out.push_back({i, j, -k, n2});
+                if (j != 0 && k != 0) out.push_back({i, -j, -k, n2});
+                if (i != 0 && k != 0) out.push_back({-i, j, -k, n2});
+                if (i != 0 && j != 0) out.push_back({-i, -j, k, n2});
+                if (i != 0 && j != 0 && k != 0) out.push_back({-i, -j, -k, n2});
+            }
+}
+
+// the 24 proper rotations of the cube as (axis permutation, signs), in the reference's order (ewald_space.cc:62-100):
+// even permutations x sign triples of product +1, then odd permutations x sign triples of product -1
+struct CubeRot {
+    signed char perm[3], sign[3];
+};
+__host__ __device__ inline CubeRot cube_rotation(int q) {
+    const signed char even[3][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}};
+    const signed char odd[3][3] = {{0, 2, 1}, {2, 1, 0}, {1, 0, 2}};
+    const signed char pos[4][3] = {{1, 1, 1}, {1, -1, -1}, {-1, 1, -1}, {-1, -1, 1}};
+    const signed char neg[4][3] = {{-1, -1, -1}, {-1, 1, 1}, {1, -1, 1}, {1, 1, -1}};
+    CubeRot r;
+    const int p = (q % 12) / 4, s = q % 4;
+    for (int c = 0; c < 3; ++c) {
+        r.perm[c] = q < 12 ? even[p][c] : odd[p][c];
+        r.sign[c] = q < 12 ? pos[s][c] : neg[s][c];
+    }
+    return r;
+}
+
+struct T3EwaldParams {
+    int ngrid;
+    double L, alpha, rel_cut, rec_cut;
+    int n_real, n_rec;
+};
+
+// D(r) at one separation (ewald_space.cc:198-286), sums in list order
+__host__ __device__ inline void t3_ewald_point(const double r[3], const T3EwaldParams &p, const EwaldIdx *__restrict__ real_idx,
+                                               const EwaldIdx *__restrict__ rec_idx, double D[3]) {
+    const double pi = 3.14159265358979323846;
+    const double L = p.L, alpha = p.alpha;
+    const double V = L * L * L;
+    const double two_alpha_over_sqrtpi = 2.0 * alpha / sqrt(pi);
+    const double fourpi_over_V = (4.0 * pi) / V;
+    const double relcutL2 = (p.rel_cut * L) * (p.rel_cut * L);
+    double fr[3] = {0.0, 0.0, 0.0}, fk[3] = {0.0, 0.0, 0.0};
+    for (int m = 0; m < p.n_real; ++m) {
+        const EwaldIdx n = real_idx[m];
+        const double Rx = r[0] + (double)n.x * L, Ry = r[1] + (double)n.y * L, Rz = r[2] + (double)n.z * L;
+        const double R2 = Rx * Rx + Ry * Ry + Rz * Rz;
+        if (R2 == 0.0 || R2 > relcutL2) continue;
+        const double R = sqrt(R2);
+        const double invR = 1.0 / R;
+        const double invR3 = invR * invR * invR;
+        const double bracket = erfc(alpha * R) + two_alpha_over_sqrtpi * R * exp(-(alpha * alpha) * R2);
+        const double coeff = invR3 * bracket;
+        fr[0] += -Rx * coeff;
+        fr[1] += -Ry * coeff;
+        fr[2] += -Rz * coeff;
+    }
+    const double factor = 2.0 * pi / L;
+    for (int m = 0; m < p.n_rec; ++m) {
+        const EwaldIdx h = rec_idx[m];
+        if (h.x == 0 && h.y == 0 && h.z == 0) continue;
+        const double kx = factor * (double)h.x, ky = factor * (double)h.y, kz = factor * (double)h.z;
+        const double k2 = kx * kx + ky * ky + kz * kz;
+        if (k2 == 0.0 || k2 > p.rec_cut * p.rec_cut) continue;
+        const double damp = exp(-k2 / (4.0 * alpha * alpha));
+        const double coeff = fourpi_over_V * damp / k2;
+        const double s = sin(kx * r[0] + ky * r[1] + kz * r[2]);
+        fk[0] += -kx * coeff * s;
+        fk[1] += -ky * coeff * s;
+        fk[2] += -kz * coeff * s;
+    }
+    const double r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    if (r2 > 0.0) {
+        const double rn = sqrt(r2);
+        const double invr3 = 1.0 / (rn * rn * rn);
+        D[0] = (fr[0] + fk[0]) - (-r[0] * invr3);
+        D[1] = (fr[1] + fk[1]) - (-r[1] * invr3);
+        D[2] = (fr[2] + fk[2]) - (-r[2] * invr3);
+    } else {
+        D[0] = D[1] = D[2] = 0.0;
+    }
+}
+
+// value at wedge point (i,j,k) and its images under the cube group (ewald_space.cc:316-376)
+__host__ __device__ inline void t3_ewald_fill(int i, int j, int k, const T3EwaldParams &p, const EwaldIdx *__restrict__ real_idx,
+                                              const EwaldIdx *__restrict__ rec_idx, double *__restrict__ table) {
+    const int N = p.ngrid;
+    const double h = p.L / (double)N;
+    const double r[3] = {((double)i + 0.5) * h - p.L / 2.0, ((double)j + 0.5) * h - p.L / 2.0, ((double)k + 0.5) * h - p.L / 2.0};
+    double Dw[3];
+    t3_ewald_point(r, p, real_idx, rec_idx, Dw);
+    auto at = [N](int a, int b, int c) { return ((size_t)((a * N + b) * N + c)) * 3u; };
+    {
+        const size_t o = at(i, j, k);
+        table[o] = Dw[0]; table[o + 1] = Dw[1]; table[o + 2] = Dw[2];
+    }
+    const int src[3] = {i, j, k};
+    for (int q = 0; q < 24; ++q) {
+        const CubeRot rot = cube_rotation(q);
+        int dst[3];
+        double Dr[3];
+        for (int d = 0; d < 3; ++d) {
+            int v = src[rot.perm[d]];
+            if (rot.sign[d] < 0) v = (N - 1) - v;  // reflection about the box centre
+            dst[d] = v;
+            Dr[d] = (double)rot.sign[d] * Dw[rot.perm[d]];
+        }
+        size_t o = at(dst[0], dst[1], dst[2]);
+        table[o] = Dr[0]; table[o + 1] = Dr[1]; table[o + 2] = Dr[2];
+        o = at((N - 1) - dst[0], (N - 1) - dst[1], (N - 1) - dst[2]);  // inversion: D(-r) = -D(r)
+        table[o] = -Dr[0]; table[o + 1] = -Dr[1]; table[o + 2] = -Dr[2];
+    }
+}
+
+// one thread per wedge point; points = packed (i, j, k) triples
+__global__ void t3_ewald_table_kernel(const int *__restrict__ points, int n_points, const T3EwaldParams p,
+                                      const EwaldIdx *__restrict__ real_idx, const EwaldIdx *__restrict__ rec_idx, double *__restrict__ table) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_points) return;
+    t3_ewald_fill(points[3 * t], points[3 * t + 1], points[3 * t + 2], p, real_idx, rec_idx, table);
+}
+
+}  // namespace steps

@@ -145,3 +145,20 @@ def test_dropin_shim_exports_the_reference_symbols_and_fails_loudly_without_gpu(
     r.configure(c.g)
     with pytest.raises(RuntimeError, match="ForceError"):
         r.forces(c.x, 0, 127)
+
+
+def test_ewald_space_counts_and_t3_defaults():
+    """host side of the T^3 Ewald table producer: the lattice enumeration of ewald_space() (ewald_space.cc:118-196) and the
+    IS_PERIODIC -> (grid, cuts) mapping of main.cc:425-446.  Counts must fit the reference's own arrays ([739], [11459])."""
+    from steps_b200 import _lib, api
+
+    lib = _lib.load()
+    assert lib.steps_b200_ewald_space_count(3.6) == 179      # rel_cut 2.6 + 1  (the reference build here reports last index 178)
+    assert lib.steps_b200_ewald_space_count(10.0) == 4139    # rec_cut 8 + 2
+    assert lib.steps_b200_ewald_space_count(5.6) <= 739 and lib.steps_b200_ewald_space_count(14.0) <= 11459
+    assert lib.steps_b200_ewald_space_count(1.0) == 1        # only the origin
+    d = api.t3_ewald_defaults(2, 100.0)
+    assert d == {"ngrid": 63, "alpha": 0.02, "rel_cut": 2.6, "rec_cut": 8.0}
+    assert api.t3_ewald_defaults(4, 50.0)["ngrid"] == 255
+    with pytest.raises(sb.StepsError):
+        api.t3_ewald_defaults(1, 100.0)

@@ -306,6 +306,39 @@ def test_t3_outside_box_takes_exact_kernel_and_large_softening():
     assert np.percentile(e, 99) < TOL64 and e.max() < 50 * TOL64
 
 
+@pytest.mark.parametrize("is_periodic,L", [(2, 30.0), (2, 100.0), (3, 100.0)])
+def test_t3_ewald_table_built_on_gpu_matches_reference_builder(is_periodic, L):
+    """calculate_t3_ewald_lookup_table on the GPU against the reference's own builder (oracle/_ref).
+    Entries near the centre are differences of terms of size 1/r^2 ~ 1/h^2, so the comparison is absolute at that scale."""
+    if not pyref.available("t3_f64"):
+        pytest.skip("reference table builder needs oracle/_ref")
+    c = ic.t3_lattice(4, 5, L=L, is_periodic=is_periodic)
+    g = c.g
+    r = pyref.Reference("t3_f64")
+    r.configure(g, 400)
+    r.build_tables()
+    r.export_tables(g)
+    n = g.N_EWALD_FORCE_GRID
+    ref = np.asarray(g.T3_EWALD_FORCE_TABLE, dtype=np.float64).reshape(n, n, n, 3).copy()
+    tab = sb.calculate_t3_ewald_lookup_table(g)
+    assert tab.shape == ref.shape and g.N_EWALD_FORCE_GRID == n
+    h = L / n
+    d = np.abs(tab - ref).max()
+    print(f"T^3 Ewald table IS_PERIODIC={is_periodic} L={L}: {n}^3, max |dD| = {d:.3e} = {d * h * h:.2e} / h^2, max |D| = {np.abs(ref).max():.3e}")
+    assert np.isfinite(tab).all()
+    assert d <= 5e-14 / (h * h)
+    assert np.abs(tab - ref).max() <= 1e-11 * np.abs(ref).max()
+
+
+def test_t3_forces_with_gpu_built_table_match_golden():
+    g, d = load_golden("t3_f64_ewald")
+    sb.calculate_t3_ewald_lookup_table(g)
+    F = gpu_forces(g, d["x"], 0, g.N - 1)
+    e = rel_err(F, d["F"])
+    print(f"t3_f64_ewald with the GPU-built table: max |dF|/|F| = {e.max():.3e}")
+    assert e.max() < TOL64
+
+
 def test_full_size_c2_properties():
     """BASELINE.json configs[1]: N = 2,000,000 FP64 compactified R^3 (size-independent properties + sampled oracle rows)"""
     c = ic.config_c2()

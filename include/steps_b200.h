@@ -105,6 +105,15 @@ int steps_b200_softening_f32(const float *M, int n, float particle_radii, float 
 int steps_b200_t3_ewald_defaults(int is_periodic, double L, int *ngrid, double *alpha, double *rel_cut, double *rec_cut);
 int steps_b200_ewald_space_count(double R);
 int steps_b200_t3_ewald_table_f64(int ngrid, double L, double alpha, double rel_cut, double rec_cut, double *table_host, int device);
+/* The S^1 x R^2 (rho, z) Ewald correction table of the lookup build: replaces calculate_S1R2ewald_correction_table() +
+ * S1R2ewald_force_pair() (ewald_space.cc:754-798, :618-752; Ewald variant) as called at main.cc:562-705.  table_host:
+ * [nrho][nz][2] doubles = (D_rho, D_z), layout of ewald_space.cc:611-614.  s1r2_ewald_defaults restates main.cc:575-605
+ * (IS_PERIODIC 2/3/>=4 -> Nz 128/256/512, nmax 4/5/IS_PERIODIC+2, mmax 10/12/IS_PERIODIC+9, alpha 0.787875/0.71805/0.6642 / L,
+ * rho_max = 2.25 Rsim, Nrho = floor(Nz * 2.25 Rsim / L)). */
+int steps_b200_s1r2_ewald_defaults(int is_periodic, double L, double Rsim, int *nrho, int *nz, double *rho_max, double *alpha, int *nmax,
+                                   int *mmax);
+int steps_b200_s1r2_ewald_table_f64(int nrho, int nz, double rho_max, double Lz, double alpha, int nmax, int mmax, double *table_host,
+                                    int device);
 
 /* ------------------------------------------------------------------------------------------
  * (2) Device-resident engine (north_star item 3): x, v, F, M, s stay in HBM across KDK steps.

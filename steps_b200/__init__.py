@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
     UNIT_T,
     UNIT_V,
     calculate_softening_length,
+    calculate_S1R2ewald_correction_table,
     calculate_t3_ewald_lookup_table,
     fma_peak,
     fma_peak_sustained,
@@ -21,5 +22,6 @@ from .api import (  # noqa: F401
     forces_periodic_z,
     friedmann_solver_step,
     partition,
+    s1r2_ewald_defaults,
     t3_ewald_defaults,
 )

@@ -228,6 +228,27 @@ def calculate_t3_ewald_lookup_table(g: Globals, device: int = 0) -> np.ndarray:
     return tab.reshape(n, n, n, 3)
 
 
+def s1r2_ewald_defaults(is_periodic: int, L: float, Rsim: float) -> dict:
+    """main.cc:575-605: dimensions and Ewald parameters of the S^1xR^2 lookup table"""
+    nrho, nz, nmax, mmax = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    rho_max, alpha = C.c_double(), C.c_double()
+    check(_lib.load().steps_b200_s1r2_ewald_defaults(is_periodic, L, Rsim, C.byref(nrho), C.byref(nz), C.byref(rho_max), C.byref(alpha),
+                                                     C.byref(nmax), C.byref(mmax)))
+    return {"nrho": nrho.value, "nz": nz.value, "rho_max": rho_max.value, "alpha": alpha.value, "nmax": nmax.value, "mmax": mmax.value}
+
+
+def calculate_S1R2ewald_correction_table(g: Globals, device: int = 0) -> np.ndarray:
+    """ewald_space.cc:754-798 on the GPU: builds S1R2_EWALD_FORCE_TABLE for g.IS_PERIODIC / g.L / g.Rsim (setup of main.cc:562-705),
+    stores it with Nrho_/Nz_EWALD_FORCE_GRID in g (REAL of the build).  Returns the FP64 table [Nrho, Nz, 2]."""
+    d = s1r2_ewald_defaults(g.IS_PERIODIC, g.L, g.Rsim)
+    tab = np.empty(d["nrho"] * d["nz"] * 2, dtype=np.float64)
+    check(_lib.load().steps_b200_s1r2_ewald_table_f64(d["nrho"], d["nz"], d["rho_max"], g.L, d["alpha"], d["nmax"], d["mmax"],
+                                                      tab.ctypes.data, device))
+    g.Nrho_EWALD_FORCE_GRID, g.Nz_EWALD_FORCE_GRID = d["nrho"], d["nz"]
+    g.S1R2_EWALD_FORCE_TABLE = np.ascontiguousarray(tab, dtype=g.REAL)
+    return tab.reshape(d["nrho"], d["nz"], 2)
+
+
 def sym_rules(n: int, nranks: int, rank: int, ib_size: int):
     """host-only rule builder of the action-reaction path: -> (i_lo, i_hi, rules[nb, 16]) or None"""
     nb_max = (n + ib_size - 1) // ib_size + 1

@@ -19,6 +19,7 @@
 #include "../../include/steps_b200.h"
 #include "aux_kernels.cuh"
 #include "ewald_t3.cuh"
+#include "ewald_s1r2.cuh"
 
 using namespace steps;
 
@@ -1244,6 +1245,47 @@ extern "C" int steps_b200_t3_ewald_table_f64(int ngrid, double L, double alpha, 
     T_TRY(cudaMemcpy(table_host, d_tab, tab_bytes, cudaMemcpyDeviceToHost));
 #undef T_TRY
     cleanup();
+    return 0;
+}
+
+// main.cc:562-605 (Ewald variant): IS_PERIODIC -> z grid, image and mode counts, alpha; Nrho from the radial extent 2.25 Rsim
+extern "C" int steps_b200_s1r2_ewald_defaults(int is_periodic, double L, double Rsim, int *nrho, int *nz, double *rho_max, double *alpha,
+                                              int *nmax, int *mmax) {
+    if (is_periodic < 2 || !(L > 0.0) || !(Rsim > 0.0)) return fail("S^1xR^2 Ewald table needs IS_PERIODIC >= 2, L > 0, Rsim > 0");
+    int z, nm, mm;
+    double al;
+    if (is_periodic == 2) { z = 128; nm = 4; mm = 10; al = 0.787875 / L; }
+    else if (is_periodic == 3) { z = 256; nm = 5; mm = 12; al = 0.71805 / L; }
+    else { z = 512; nm = is_periodic + 2; mm = is_periodic + 9; al = 0.6642 / L; }
+    const double extent = 2.25;  // EWALD_LOOKUP_TABLE_RADIAL_EXTENT_FACTOR (global_variables.h:39)
+    if (nz) *nz = z;
+    if (nrho) *nrho = (int)floor(((double)z) * extent * Rsim / L);
+    if (rho_max) *rho_max = extent * Rsim;
+    if (alpha) *alpha = al;
+    if (nmax) *nmax = nm;
+    if (mmax) *mmax = mm;
+    return 0;
+}
+
+extern "C" int steps_b200_s1r2_ewald_table_f64(int nrho, int nz, double rho_max, double Lz, double alpha, int nmax, int mmax,
+                                               double *table_host, int device) {
+    if (!table_host) return fail("table is NULL");
+    if (nrho < 1 || nz < 1 || (long long)nrho * nz > (1LL << 28)) return fail("bad table dimensions");
+    if (!(rho_max > 0.0) || !(Lz > 0.0) || !(alpha > 0.0) || nmax < 0 || mmax < 0) return fail("bad S^1xR^2 Ewald parameters");
+    int ndev = steps_b200_device_count();
+    if (ndev == 0) return fail("no CUDA device available: libstepsb200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("bad device ordinal");
+    DeviceGuard dg_;
+    CU_TRY(cudaSetDevice(device));
+    const S1R2EwaldParams p{nrho, nz, nmax, mmax, rho_max, Lz, alpha};
+    const size_t bytes = (size_t)nrho * nz * 2 * sizeof(double);
+    double *d_tab = nullptr;
+    CU_TRY(cudaMalloc(&d_tab, bytes));
+    s1r2_ewald_table_kernel<<<(nrho * nz + 127) / 128, 128>>>(p, d_tab);
+    cudaError_t e1 = cudaGetLastError();
+    cudaError_t e2 = e1 == cudaSuccess ? cudaMemcpy(table_host, d_tab, bytes, cudaMemcpyDeviceToHost) : e1;
+    cudaFree(d_tab);
+    if (e2 != cudaSuccess) return fail(std::string("CUDA error: ") + cudaGetErrorString(e2) + " in steps_b200_s1r2_ewald_table_f64");
     return 0;
 }
 

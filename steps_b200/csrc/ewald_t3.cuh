@@ -118,12 +118,24 @@ __host__ __device__ inline void t3_ewald_point(const double r[3], const T3EwaldP
     }
 }
 
+__host__ __device__ inline double t3_cell_centre(int i, double h, double L) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(__dmul_rn((double)i + 0.5, h), -(L / 2.0));
+#else
+    volatile double prod = ((double)i + 0.5) * h;  // volatile: no contraction on hosts that have FMA either
+    return prod - L / 2.0;
+#endif
+}
+
 // value at wedge point (i,j,k) and its images under the cube group (ewald_space.cc:316-376)
 __host__ __device__ inline void t3_ewald_fill(int i, int j, int k, const T3EwaldParams &p, const EwaldIdx *__restrict__ real_idx,
                                               const EwaldIdx *__restrict__ rec_idx, double *__restrict__ table) {
     const int N = p.ngrid;
     const double h = p.L / (double)N;
-    const double r[3] = {((double)i + 0.5) * h - p.L / 2.0, ((double)j + 0.5) * h - p.L / 2.0, ((double)k + 0.5) * h - p.L / 2.0};
+    // cell-centre coordinate (i + 1/2) h - L/2, product and difference rounded separately as in the reference build.  A fused
+    // multiply-add would leave ~1e-15 instead of 0 on the symmetry planes (i = N/2 of the odd grid), and at the centre point
+    // that turns D = 0 (ewald_space.cc:280-283) into the difference of two terms of size 1/r^2 = 1e30.
+    const double r[3] = {t3_cell_centre(i, h, p.L), t3_cell_centre(j, h, p.L), t3_cell_centre(k, h, p.L)};
     double Dw[3];
     t3_ewald_point(r, p, real_idx, rec_idx, Dw);
     auto at = [N](int a, int b, int c) { return ((size_t)((a * N + b) * N + c)) * 3u; };

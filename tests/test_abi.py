@@ -162,3 +162,14 @@ def test_ewald_space_counts_and_t3_defaults():
     assert api.t3_ewald_defaults(4, 50.0)["ngrid"] == 255
     with pytest.raises(sb.StepsError):
         api.t3_ewald_defaults(1, 100.0)
+
+
+def test_s1r2_ewald_defaults():
+    """main.cc:575-605 restated: table dimensions and Ewald parameters of the S^1xR^2 lookup build"""
+    from steps_b200 import api
+
+    d = api.s1r2_ewald_defaults(2, 20.0, 30.0)
+    assert (d["nz"], d["nrho"], d["nmax"], d["mmax"]) == (128, 432, 4, 10)
+    assert d["rho_max"] == 67.5 and abs(d["alpha"] - 0.787875 / 20.0) < 1e-18
+    d = api.s1r2_ewald_defaults(5, 100.0, 500.0)
+    assert (d["nz"], d["nmax"], d["mmax"]) == (512, 7, 14)

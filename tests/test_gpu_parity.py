@@ -339,6 +339,34 @@ def test_t3_forces_with_gpu_built_table_match_golden():
     assert e.max() < TOL64
 
 
+def test_s1r2_ewald_table_built_on_gpu_matches_reference_builder_and_golden_forces():
+    """calculate_S1R2ewald_correction_table on the GPU against the reference's own builder, then the golden
+    lookup-build forces with the GPU-built table"""
+    if not pyref.available("s1r2_f64"):
+        pytest.skip("reference table builder needs oracle/_ref")
+    c = ic.s1r2_cylinder(3000, 24, 80, 63, lookup=True, is_periodic=2, L=20.0, r_sim=30.0, d_s=8.0, r_crit=10.0)
+    g = c.g
+    r = pyref.Reference("s1r2_f64")
+    r.configure(g, 400)
+    r.build_tables()
+    r.export_tables(g)
+    nrho, nz = g.Nrho_EWALD_FORCE_GRID, g.Nz_EWALD_FORCE_GRID
+    ref = np.asarray(g.S1R2_EWALD_FORCE_TABLE, dtype=np.float64).reshape(nrho, nz, 2).copy()
+    tab = sb.calculate_S1R2ewald_correction_table(g)
+    assert tab.shape == ref.shape
+    dz = g.L / nz
+    d = np.abs(tab - ref).max()
+    print(f"S1R2 Ewald table {nrho}x{nz}: max |dD| = {d:.3e} (scale 4/dz^2 = {4 / dz**2:.1f}), max |D| = {np.abs(ref).max():.3e}")
+    assert np.isfinite(tab).all()
+    assert d <= 1e-15 * 4 / dz**2
+    g2, gold = load_golden("s1r2_f64_lookup")
+    sb.calculate_S1R2ewald_correction_table(g2)
+    F = gpu_forces(g2, gold["x"], 0, g2.N - 1)
+    e = rel_err(F, gold["F"])
+    print(f"s1r2_f64_lookup with the GPU-built table: max |dF|/|F| = {e.max():.3e}")
+    assert e.max() < TOL64
+
+
 def test_full_size_c2_properties():
     """BASELINE.json configs[1]: N = 2,000,000 FP64 compactified R^3 (size-independent properties + sampled oracle rows)"""
     c = ic.config_c2()

@@ -20,7 +20,13 @@ for ip in (2, 3, 4, 2, 3, 4):
     tab = np.empty(n * n * n * 3)
     t0 = time.perf_counter()
     _lib.check(lib.steps_b200_t3_ewald_table_f64(n, 100.0, d["alpha"], d["rel_cut"], d["rec_cut"], tab.ctypes.data, 0))
-    print(f"IS_PERIODIC={ip}: {n}^3 table in {time.perf_counter() - t0:.3f} s (call incl. alloc + D2H), checksum {np.abs(tab).sum():.12e}", flush=True)
+    print(f"T^3 IS_PERIODIC={ip}: {n}^3 table in {time.perf_counter() - t0:.3f} s (call incl. alloc + D2H), checksum {np.abs(tab).sum():.12e}", flush=True)
+for ip in (2, 3, 4):
+    d = sb.s1r2_ewald_defaults(ip, 100.0, 500.0)
+    tab = np.empty(d["nrho"] * d["nz"] * 2)
+    t0 = time.perf_counter()
+    _lib.check(lib.steps_b200_s1r2_ewald_table_f64(d["nrho"], d["nz"], d["rho_max"], 100.0, d["alpha"], d["nmax"], d["mmax"], tab.ctypes.data, 0))
+    print(f"S1R2 IS_PERIODIC={ip}: {d['nrho']}x{d['nz']} table in {time.perf_counter() - t0:.3f} s, checksum {np.abs(tab).sum():.12e}", flush=True)
 PY
 cat $O/${TAG}_table_build_times.txt
 stamp "full regression"

@@ -114,6 +114,10 @@ int steps_b200_s1r2_ewald_defaults(int is_periodic, double L, double Rsim, int *
                                    int *mmax);
 int steps_b200_s1r2_ewald_table_f64(int nrho, int nz, double rho_max, double Lz, double alpha, int nmax, int mmax, double *table_host,
                                     int device);
+/* RADIAL_FORCE_TABLE of the S^1 x R^2 builds: replaces get_cylindrical_force_table(FORCE_TABLE, R, Lz, TABLE_SIZE,
+ * RADIAL_FORCE_ACCURACY) (utils.cc:162-228), called with R = Rsim and Lz = L/2 (IS_PERIODIC == 1) or Lz = L * ewald_cut,
+ * ewald_cut = IS_PERIODIC + 1 - 0.4 (NOLOOKUP build, IS_PERIODIC >= 2) at main.cc:1263-1310. */
+int steps_b200_radial_force_table_f64(double R, double Lz, int table_size, int accuracy, double *table_host, int device);
 
 /* ------------------------------------------------------------------------------------------
  * (2) Device-resident engine (north_star item 3): x, v, F, M, s stay in HBM across KDK steps.

@@ -21,6 +21,7 @@ from .api import (  # noqa: F401
     forces_periodic,
     forces_periodic_z,
     friedmann_solver_step,
+    get_cylindrical_force_table,
     partition,
     s1r2_ewald_defaults,
     t3_ewald_defaults,

@@ -71,6 +71,7 @@ SYMBOLS = {
     "steps_b200_t3_ewald_table_f64": (_I, [_I, _D, _D, _D, _D, _VP, _I]),
     "steps_b200_s1r2_ewald_defaults": (_I, [_I, _D, _D, _PI, _PI, _PD, _PD, _PI, _PI]),
     "steps_b200_s1r2_ewald_table_f64": (_I, [_I, _I, _D, _D, _D, _I, _I, _VP, _I]),
+    "steps_b200_radial_force_table_f64": (_I, [_D, _D, _I, _I, _VP, _I]),
     "steps_b200_engine_create": (_I, [C.POINTER(_VP), _PP, _I, _I]),
     "steps_b200_engine_destroy": (None, [_VP]),
     "steps_b200_partition": (None, [_I, _I, _I, _PI, _PI]),

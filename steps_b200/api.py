@@ -249,6 +249,16 @@ def calculate_S1R2ewald_correction_table(g: Globals, device: int = 0) -> np.ndar
     return tab.reshape(d["nrho"], d["nz"], 2)
 
 
+def get_cylindrical_force_table(g: Globals, accuracy: int = 7500, device: int = 0) -> np.ndarray:
+    """utils.cc:162-228 on the GPU: RADIAL_FORCE_TABLE for g (S^1xR^2), with the Lz the reference passes at main.cc:1263-1310:
+    L/2 in the quasi-periodic mode (IS_PERIODIC == 1), L * (IS_PERIODIC + 1 - 0.4) in the NOLOOKUP image-sum mode."""
+    Lz = 0.5 * g.L if g.IS_PERIODIC == 1 else g.L * ((g.IS_PERIODIC + 1) - 0.4)
+    tab = np.empty(g.RADIAL_FORCE_TABLE_SIZE, dtype=np.float64)
+    check(_lib.load().steps_b200_radial_force_table_f64(g.Rsim, Lz, g.RADIAL_FORCE_TABLE_SIZE, accuracy, tab.ctypes.data, device))
+    g.RADIAL_FORCE_TABLE = np.ascontiguousarray(tab, dtype=g.REAL)
+    return tab
+
+
 def sym_rules(n: int, nranks: int, rank: int, ib_size: int):
     """host-only rule builder of the action-reaction path: -> (i_lo, i_hi, rules[nb, 16]) or None"""
     nb_max = (n + ib_size - 1) // ib_size + 1

@@ -20,6 +20,7 @@
 #include "aux_kernels.cuh"
 #include "ewald_t3.cuh"
 #include "ewald_s1r2.cuh"
+#include "radial_table.cuh"
 
 using namespace steps;
 
@@ -1286,6 +1287,28 @@ extern "C" int steps_b200_s1r2_ewald_table_f64(int nrho, int nz, double rho_max,
     cudaError_t e2 = e1 == cudaSuccess ? cudaMemcpy(table_host, d_tab, bytes, cudaMemcpyDeviceToHost) : e1;
     cudaFree(d_tab);
     if (e2 != cudaSuccess) return fail(std::string("CUDA error: ") + cudaGetErrorString(e2) + " in steps_b200_s1r2_ewald_table_f64");
+    return 0;
+}
+
+extern "C" int steps_b200_radial_force_table_f64(double R, double Lz, int table_size, int accuracy, double *table_host, int device) {
+    if (!table_host) return fail("table is NULL");
+    if (table_size < 1 || accuracy < 1 || !(R > 0.0) || !(Lz > 0.0)) return fail("bad radial force table parameters");
+    int ndev = steps_b200_device_count();
+    if (ndev == 0) return fail("no CUDA device available: libstepsb200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("bad device ordinal");
+    DeviceGuard dg_;
+    CU_TRY(cudaSetDevice(device));
+    double *d_tab = nullptr;
+    CU_TRY(cudaMalloc(&d_tab, (size_t)table_size * sizeof(double)));
+    cudaError_t err = cudaMemset(d_tab, 0, (size_t)table_size * sizeof(double));  // FORCE_TABLE[0] = 0.0 (utils.cc:170)
+    if (err == cudaSuccess) {
+        radial_table_kernel<<<(table_size + 63) / 64, 64>>>(R, Lz, table_size, accuracy, d_tab);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpy(table_host, d_tab, (size_t)table_size * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_tab);
+    if (err != cudaSuccess) return fail(std::string("CUDA error: ") + cudaGetErrorString(err) + " in steps_b200_radial_force_table_f64");
+    if (table_size >= 3) table_host[0] = radial_table_origin(R, table_size, table_host[1], table_host[2]);  // utils.cc:223-227
     return 0;
 }
 

@@ -7,7 +7,7 @@ export PYTHONUNBUFFERED=1
 t0=$(date +%s)
 stamp() { echo "[$(( $(date +%s) - t0 ))s] $*" | tee -a $O/${TAG}_timeline.txt; }
 stamp "T^3 Ewald table builder tests"
-timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q -s --timeout 300 -k "ewald_table or gpu_built_table" > $O/${TAG}_table_tests.log 2>&1
+timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q -s --timeout 300 -k "ewald_table or gpu_built_table or radial_force_table" > $O/${TAG}_table_tests.log 2>&1
 echo "rc=$?" >> $O/${TAG}_table_tests.log; grep -E "T\^3|t3_|passed|failed|rc=|Error" $O/${TAG}_table_tests.log | cut -c1-220 | tail -12
 stamp "table build time 63^3 / 127^3 / 255^3 on the GPU"
 timeout 200 python - > $O/${TAG}_table_build_times.txt 2>&1 <<'PY'

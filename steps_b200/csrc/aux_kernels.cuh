@@ -5,6 +5,7 @@
 #include "pair_r3_f32.cuh"
 #include "pair_s1r2.cuh"
 #include "pair_r3_sym.cuh"
+#include "pair_r3_sym_f32.cuh"
 
 namespace steps {
 

@@ -228,7 +228,7 @@ struct steps_b200_engine {
     int sym_ib = 0;              // i-block size of the symmetric kernel shape
     std::vector<SymRule> h_rules;  // one per local i-block of [i_lo, i_hi)
     SymRule *d_rules = nullptr;
-    double *d_gpart = nullptr, *d_fsym = nullptr;
+    void *d_gpart = nullptr, *d_fsym = nullptr;  // REAL of the build
     size_t gpart_bytes = 0;
 };
 
@@ -377,6 +377,33 @@ bool sym_env_default() {
     return v == 1;
 }
 constexpr int SYM_TARGET_CHUNKS = 56;
+// FP32 shapes of the action-reaction kernel (pair_r3_sym_f32.cuh); STEPS_B200_SYM_F32_VARIANT=k
+constexpr SymVariant SYM32_VARIANTS[] = {
+    {8, 128, 4, 2},   // 0: i-block 1024, <= 128 registers, 16 warps/SM
+    {16, 128, 2, 2},  // 1: i-block 2048, <= 255 registers, 8 warps/SM
+    {12, 128, 3, 2},  // 2: i-block 1536, <= 170 registers, 12 warps/SM
+};
+constexpr int N_SYM32_VARIANTS = sizeof(SYM32_VARIANTS) / sizeof(SYM32_VARIANTS[0]);
+int sym32_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("STEPS_B200_SYM_F32_VARIANT");
+        v = s ? atoi(s) : 0;
+        if (v < 0 || v >= N_SYM32_VARIANTS) v = 0;
+    }
+    return v;
+}
+// The FP32 build takes the action-reaction path by default too (measured 2.75e12 against 1.90e12 interactions/s at N = 2M and closer
+// to FP64 truth than the one-sided kernel, profiles/r1aa_*); STEPS_B200_SYM=0 or STEPS_B200_SYM_F32=0 keeps it on the one-sided kernel.
+bool sym_f32_env_default() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("STEPS_B200_SYM_F32");
+        v = (s && atoi(s) == 0) ? 0 : 1;
+    }
+    return v == 1 && sym_env_default();
+}
+SymVariant sym_shape(const steps_b200_engine *e) { return e->real_bytes == 8 ? SYM_VARIANTS[sym_variant()] : SYM32_VARIANTS[sym32_variant()]; }
 
 // i-blocks [blo, bhi) of rank r when nb_total blocks are dealt out contiguously, remainder one-each to the first ranks
 void sym_block_range(int nb_total, int nranks, int r, int &blo, int &bhi) {
@@ -453,8 +480,8 @@ int setup_partition(steps_b200_engine *e, bool want_sym) {
     e->sym = false;
     e->h_rules.clear();
     steps_b200_partition(e->n, e->nranks, e->rank, &e->i_lo, &e->i_hi);
-    if (!want_sym || e->real_bytes != 8 || e->p.topology != STEPS_TOPO_R3) return 0;
-    const SymVariant sv = SYM_VARIANTS[sym_variant()];
+    if (!want_sym || e->p.topology != STEPS_TOPO_R3) return 0;
+    const SymVariant sv = sym_shape(e);
     const int ib = sv.R * sv.threads;
     int lo, hi;
     std::vector<SymRule> rules;
@@ -492,7 +519,7 @@ bool sym_call(const steps_b200_engine *e, int id_min, int n_i) {
 }
 
 Plan sym_plan(const steps_b200_engine *e, int n_i) {
-    const SymVariant sv = SYM_VARIANTS[sym_variant()];
+    const SymVariant sv = sym_shape(e);
     Plan p{};
     p.ib_size = sv.R * sv.threads;
     p.n_ib = (n_i + p.ib_size - 1) / p.ib_size;
@@ -650,24 +677,31 @@ int launch_pair(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
 
 
 // last phase of the action-reaction evaluation: chunk sums of the i side - j-side sums + background term -> F
-int finish_pair_sym(steps_b200_engine *e, int id_min, int n_i, const Plan &pl) {
-    reduce_kernel<double><<<(n_i + 255) / 256, 256, 0, e->stream>>>(static_cast<const double *>(e->d_fpart), pl.n_chunks, n_i, n_i, id_min,
-                                                                     static_cast<const double *>(e->d_x), static_cast<double *>(e->d_F), e->tp,
-                                                                     e->d_fsym, (size_t)e->n_pad);
+template <typename T>
+int finish_pair_sym_t(steps_b200_engine *e, int id_min, int n_i, const Plan &pl) {
+    reduce_kernel<T><<<(n_i + 255) / 256, 256, 0, e->stream>>>(static_cast<const T *>(e->d_fpart), pl.n_chunks, n_i, n_i, id_min,
+                                                                static_cast<const T *>(e->d_x), static_cast<T *>(e->d_F), e->tp,
+                                                                static_cast<const T *>(e->d_fsym), (size_t)e->n_pad);
     e->launches++;
     CU_TRY(cudaGetLastError());
     return 0;
+}
+int finish_pair_sym(steps_b200_engine *e, int id_min, int n_i, const Plan &pl) {
+    return e->real_bytes == 8 ? finish_pair_sym_t<double>(e, id_min, n_i, pl) : finish_pair_sym_t<float>(e, id_min, n_i, pl);
 }
 
 // Force evaluation of the engine's own rows by the action-reaction kernel: passes over groups of i-blocks (bounded
 // j-side partial buffer), each pass = pair kernel + j-side row reduction; then (multi-GPU) one all-reduce of the
 // j-side sums, then the usual chunk reduction, which also subtracts the j-side sum and adds the background term.
+template <typename T>
 int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
-    const SymVariant sv = SYM_VARIANTS[sym_variant()];
+    using JRec = typename JRecOf<T>::type;
+    constexpr bool F64 = sizeof(T) == 8;
+    const SymVariant sv = sym_shape(e);
     const Plan pl = sym_plan(e, n_i);
     plan_out = pl;
     if ((int)e->h_rules.size() != pl.n_ib) return fail("symmetric path: rule table does not match the i-range");
-    const size_t need = (size_t)pl.n_chunks * 3 * (size_t)n_i * sizeof(double);
+    const size_t need = (size_t)pl.n_chunks * 3 * (size_t)n_i * sizeof(T);
     if (need > e->fpart_bytes) {
         if (e->d_fpart) CU_TRY(cudaFree(e->d_fpart));
         e->d_fpart = nullptr;
@@ -675,7 +709,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         CU_TRY(cudaMalloc(&e->d_fpart, need));
         e->fpart_bytes = need;
     }
-    const size_t row_bytes = (size_t)3 * e->n_pad * sizeof(double);
+    const size_t row_bytes = (size_t)3 * e->n_pad * sizeof(T);
     if (!e->d_fsym) CU_TRY(cudaMalloc(&e->d_fsym, row_bytes));
     if (!e->d_gpart) {
         size_t free_b = 0, total_b = 0;
@@ -684,7 +718,17 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         if (const char *s = getenv("STEPS_B200_SYM_GPART_MB")) budget = (size_t)atoll(s) << 20;
         size_t rows = std::max<size_t>(1, budget / row_bytes);
         rows = std::min<size_t>(rows, (size_t)pl.n_ib);
-        CU_TRY(cudaMalloc(&e->d_gpart, rows * row_bytes));
+        // a smaller buffer only means more passes: halve until the allocation succeeds
+        cudaError_t err = cudaErrorMemoryAllocation;
+        while (rows >= 1) {
+            err = cudaMalloc(&e->d_gpart, rows * row_bytes);
+            if (err == cudaSuccess) break;
+            cudaGetLastError();
+            e->d_gpart = nullptr;
+            if (rows == 1) break;
+            rows = (rows + 1) / 2;
+        }
+        if (err != cudaSuccess) return fail(std::string("CUDA error: ") + cudaGetErrorString(err) + " allocating the j-side row buffer");
         e->gpart_bytes = rows * row_bytes;
     }
     const int rows = (int)(e->gpart_bytes / row_bytes);
@@ -702,9 +746,15 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     sa.rules = e->d_rules;
     sa.gpart = e->d_gpart;
     sa.n_pad = e->n_pad;
-    const size_t smem = (size_t)F64_STAGES * (F64_TJ * sizeof(JRec64) + sizeof(TileInfo64)) + (size_t)(sv.threads / 32) * sizeof(WarpBounds64) +
-                        (size_t)2 * (sv.threads / 32) * 3 * F64_TJ * sizeof(double) + (size_t)8 * F64_TJ * sizeof(double) +
-                        2 * F64_STAGES * sizeof(uint64_t);
+    const int nwarps = sv.threads / 32;
+    // staged tiles + tile bounds | warp bounds | visiting copy (x,y,z,m of each record twice) | 2 x per-warp accumulator slots | barriers
+    const size_t smem = F64 ? (size_t)F64_STAGES * (F64_TJ * sizeof(JRec64) + sizeof(TileInfo64)) + (size_t)nwarps * sizeof(WarpBounds64) +
+                                  (size_t)2 * nwarps * 3 * F64_TJ * sizeof(double) + (size_t)8 * F64_TJ * sizeof(double) +
+                                  2 * F64_STAGES * sizeof(uint64_t)
+                            : (size_t)F64_STAGES * (F64_TJ * sizeof(JRec32) + sizeof(TileInfo32)) + (size_t)nwarps * sizeof(WarpBounds32) +
+                                  (size_t)2 * F64_TJ * sizeof(float4) + (size_t)2 * nwarps * 3 * F64_TJ * sizeof(float) +
+                                  2 * F64_STAGES * sizeof(uint64_t);
+    (void)sizeof(JRec);
     CU_TRY(cudaEventRecord(e->ev[4], e->stream));
     for (int b0 = 0; b0 < pl.n_ib; b0 += rows) {
         const int nb = std::min(rows, pl.n_ib - b0);
@@ -717,19 +767,32 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
         kern<<<nb * pl.n_chunks, SYM_VARIANTS[K].threads, smem, e->stream>>>(sa);                                      \
     } break;
-        switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) LAUNCH_SYM(3) }
+#define LAUNCH_SYM32(K)                                                                                                \
+    case K: {                                                                                                          \
+        auto kern = force_r3_f32_sym_kernel<SYM32_VARIANTS[K].R, SYM32_VARIANTS[K].threads, F64_TJ, F64_STAGES,        \
+                                            SYM32_VARIANTS[K].minb, SYM32_VARIANTS[K].unroll>;                         \
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        kern<<<nb * pl.n_chunks, SYM32_VARIANTS[K].threads, smem, e->stream>>>(sa);                                    \
+    } break;
+        if (F64) {
+            switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) LAUNCH_SYM(3) }
+        } else {
+            switch (sym32_variant()) { LAUNCH_SYM32(0) LAUNCH_SYM32(1) LAUNCH_SYM32(2) }
+        }
 #undef LAUNCH_SYM
+#undef LAUNCH_SYM32
         e->launches++;
         CU_TRY(cudaGetLastError());
-        reduce_sym_kernel<<<(e->n_pad + 255) / 256, 256, 0, e->stream>>>(e->d_gpart, e->d_rules, b0, nb, e->n_pad, TJ, e->d_fsym);
+        reduce_sym_kernel<T><<<(e->n_pad + 255) / 256, 256, 0, e->stream>>>(static_cast<const T *>(e->d_gpart), e->d_rules, b0, nb, e->n_pad, TJ,
+                                                                             static_cast<T *>(e->d_fsym));
         e->launches++;
         CU_TRY(cudaGetLastError());
     }
     CU_TRY(cudaEventRecord(e->ev[5], e->stream));
-    // multi-GPU: the j-side sums a rank formed for other ranks' particles travel in ONE all-reduce (3 n_pad doubles).
+    // multi-GPU: the j-side sums a rank formed for other ranks' particles travel in ONE all-reduce (3 n_pad REALs).
     // (An engine given a rank without a communicator -- the single-GPU test hook -- skips it: the test sums on the host.)
     if (e->nranks > 1 && e->comm)
-        NCCL_TRY(g_nccl.AllReduce(e->d_fsym, e->d_fsym, (size_t)3 * e->n_pad, ncclFloat64, ncclSum, e->comm, e->stream));
+        NCCL_TRY(g_nccl.AllReduce(e->d_fsym, e->d_fsym, (size_t)3 * e->n_pad, F64 ? ncclFloat64 : ncclFloat32, ncclSum, e->comm, e->stream));
     return finish_pair_sym(e, id_min, n_i, pl);
 }
 
@@ -762,7 +825,7 @@ int forces_impl(steps_b200_engine *e, int id_min, int id_max) {
     Plan pl;
     const int n_i = id_max - id_min + 1;
     int rc;
-    if (sym_call(e, id_min, n_i)) rc = launch_pair_sym(e, id_min, n_i, pl);
+    if (sym_call(e, id_min, n_i)) rc = (e->real_bytes == 8) ? launch_pair_sym<double>(e, id_min, n_i, pl) : launch_pair_sym<float>(e, id_min, n_i, pl);
     else rc = (e->real_bytes == 8) ? launch_pair<double>(e, id_min, n_i, pl) : launch_pair<float>(e, id_min, n_i, pl);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(e->ev[1], e->stream));
@@ -873,7 +936,7 @@ extern "C" int steps_b200_engine_create(steps_b200_engine **out, const steps_b20
     for (auto &ev : e->ev) E_TRY(cudaEventCreate(&ev));
     for (auto &ev : e->marks) E_TRY(cudaEventCreate(&ev));
 #undef E_TRY
-    if (upload_tables(e) || setup_partition(e, sym_env_default())) {
+    if (upload_tables(e) || setup_partition(e, real_bytes == 8 ? sym_env_default() : sym_f32_env_default())) {
         steps_b200_engine_destroy(e);
         return 1;
     }
@@ -942,14 +1005,14 @@ extern "C" int steps_b200_engine_debug_set_rank(steps_b200_engine *e, int rank, 
     return setup_partition(e, symmetric != 0);
 }
 
-extern "C" int steps_b200_engine_debug_fsym(steps_b200_engine *e, double *fsym_out, const double *fsym_in, int *n_pad_out) {
+extern "C" int steps_b200_engine_debug_fsym(steps_b200_engine *e, void *fsym_out, const void *fsym_in, int *n_pad_out) {
     if (!e) return fail("engine is NULL");
     if (n_pad_out) *n_pad_out = e->n_pad;
     if (!fsym_out && !fsym_in) return 0;
     if (!e->sym || !e->d_fsym) return fail("no action-reaction evaluation has run on this engine");
     DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
-    const size_t bytes = (size_t)3 * e->n_pad * sizeof(double);
+    const size_t bytes = (size_t)3 * e->n_pad * e->real_bytes;
     if (fsym_out) {
         CU_TRY(cudaMemcpyAsync(fsym_out, e->d_fsym, bytes, cudaMemcpyDeviceToHost, e->stream));
         CU_TRY(cudaStreamSynchronize(e->stream));
@@ -979,7 +1042,7 @@ extern "C" int steps_b200_engine_comm_init(steps_b200_engine *e, const void *id1
     e->nranks = nranks;
     DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
-    if (setup_partition(e, e->sym || sym_env_default())) return 1;
+    if (setup_partition(e, e->sym || (e->real_bytes == 8 ? sym_env_default() : sym_f32_env_default()))) return 1;
     if (nranks == 1) return 0;
     if (nccl_load()) return 1;
     ncclUniqueId id;

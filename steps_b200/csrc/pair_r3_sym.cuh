@@ -46,7 +46,7 @@ struct SymLaunchArgs {
     R3LaunchArgs a;        // jrec/tinfo/fpart/id_min/n_i/tiles_per_chunk/n_tiles/n_j/fstride as for the one-sided kernel;
                            // a.n_ib = number of i-blocks in THIS launch (a pass)
     const SymRule *rules;  // one per local i-block (index 0 = the block starting at id_min)
-    double *gpart;         // j-side partial rows: [i-block of the pass][3][n_pad]
+    void *gpart;           // j-side partial rows: [i-block of the pass][3][n_pad], REAL of the build
     int b0;                // first local i-block of this pass
     int n_pad;             // n_tiles * TJ
 };
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_sym_kernel(const S
                 __syncthreads();
                 if (tid < TJ) {
                     const double *__restrict__ sb = slots + (size_t)(nsym & 1) * NWARPS * 3 * TJ;
-                    double *__restrict__ gp = sa.gpart + (size_t)gb * 3 * sa.n_pad + (size_t)(t0 + t) * TJ + tid;
+                    double *__restrict__ gp = static_cast<double *>(sa.gpart) + (size_t)gb * 3 * sa.n_pad + (size_t)(t0 + t) * TJ + tid;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         double v = 0.0;
@@ -382,15 +382,16 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f64_sym_kernel(const S
 
 // j-side reduction of one pass: fsym[c][j] += sum over the pass's i-blocks (in block order) of the rows that hold a
 // symmetric contribution for j's tile.  One thread per j.
-__global__ void reduce_sym_kernel(const double *__restrict__ gpart, const SymRule *__restrict__ rules, int b0, int nb, int n_pad,
-                                  int tj, double *__restrict__ fsym) {
+template <typename T>
+__global__ void reduce_sym_kernel(const T *__restrict__ gpart, const SymRule *__restrict__ rules, int b0, int nb, int n_pad, int tj,
+                                  T *__restrict__ fsym) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_pad) return;
     const int t = j / tj;
-    double sx = 0.0, sy = 0.0, sz = 0.0;
+    T sx = 0, sy = 0, sz = 0;
     for (int g = 0; g < nb; ++g) {
         if (sym_tile_class(rules[b0 + g], t) == 2) {
-            const double *__restrict__ row = gpart + (size_t)g * 3 * n_pad + j;
+            const T *__restrict__ row = gpart + (size_t)g * 3 * n_pad + j;
             sx += row[0];
             sy += row[(size_t)n_pad];
             sz += row[2 * (size_t)n_pad];

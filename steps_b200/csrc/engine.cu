@@ -403,7 +403,43 @@ bool sym_f32_env_default() {
     }
     return v == 1 && sym_env_default();
 }
-SymVariant sym_shape(const steps_b200_engine *e) { return e->real_bytes == 8 ? SYM_VARIANTS[sym_variant()] : SYM32_VARIANTS[sym32_variant()]; }
+// Shapes of the S^1xR^2 action-reaction kernel (pair_s1r2_sym.cuh); STEPS_B200_S1R2_SYM_VARIANT=k
+constexpr SymVariant S1R2_SYM_VARIANTS[] = {
+    {3, 128, 4, 1},  // 0: i-block 384, <= 128 registers, 16 warps/SM
+    {2, 128, 5, 1},  // 1: i-block 256, <= 102 registers, 20 warps/SM
+    {4, 128, 3, 1},  // 2: i-block 512, <= 168 registers, 12 warps/SM
+    {3, 128, 4, 2},  // 3: shape 0 with the visiting steps unrolled by 2
+};
+constexpr int N_S1R2_SYM_VARIANTS = sizeof(S1R2_SYM_VARIANTS) / sizeof(S1R2_SYM_VARIANTS[0]);
+int s1r2_sym_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("STEPS_B200_S1R2_SYM_VARIANT");
+        v = s ? atoi(s) : 0;
+        if (v < 0 || v >= N_S1R2_SYM_VARIANTS) v = 0;
+    }
+    return v;
+}
+// OPT-IN (STEPS_B200_S1R2_SYM=1, or an explicit steps_b200_engine_set_symmetric(e, 1)): the kernel was written after the round's GPU
+// budget was spent and has not run on a GPU yet.
+bool s1r2_sym_env_default() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("STEPS_B200_S1R2_SYM");
+        v = (s && atoi(s) != 0) ? 1 : 0;
+    }
+    return v == 1 && sym_env_default();
+}
+SymVariant sym_shape(const steps_b200_engine *e) {
+    if (e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP) return S1R2_SYM_VARIANTS[s1r2_sym_variant()];
+    return e->real_bytes == 8 ? SYM_VARIANTS[sym_variant()] : SYM32_VARIANTS[sym32_variant()];
+}
+// whether an engine takes the action-reaction path when the caller has not said so
+bool sym_default_for(const steps_b200_engine *e) {
+    if (e->p.topology == STEPS_TOPO_R3) return e->real_bytes == 8 ? sym_env_default() : sym_f32_env_default();
+    if (tuned_s1r2(e)) return s1r2_sym_env_default();
+    return false;
+}
 
 // i-blocks [blo, bhi) of rank r when nb_total blocks are dealt out contiguously, remainder one-each to the first ranks
 void sym_block_range(int nb_total, int nranks, int r, int &blo, int &bhi) {
@@ -480,7 +516,7 @@ int setup_partition(steps_b200_engine *e, bool want_sym) {
     e->sym = false;
     e->h_rules.clear();
     steps_b200_partition(e->n, e->nranks, e->rank, &e->i_lo, &e->i_hi);
-    if (!want_sym || e->p.topology != STEPS_TOPO_R3) return 0;
+    if (!want_sym || !(e->p.topology == STEPS_TOPO_R3 || tuned_s1r2(e))) return 0;
     const SymVariant sv = sym_shape(e);
     const int ib = sv.R * sv.threads;
     int lo, hi;
@@ -774,7 +810,29 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
         kern<<<nb * pl.n_chunks, SYM32_VARIANTS[K].threads, smem, e->stream>>>(sa);                                    \
     } break;
-        if (F64) {
+        if (F64 && e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP) {
+            S1R2Consts k{};
+            k.L = e->tp.L;
+            k.cut = e->tp.ewald_cut * e->tp.L;
+            k.M = e->tp.ewald_max;
+            if (k.M < 3 || k.M > 5) return fail("S^1xR^2 action-reaction kernel: unsupported IS_PERIODIC");
+#define LAUNCH_S1R2_SYM_VM(V, MM)                                                                                                   \
+    {                                                                                                                               \
+        auto kern = force_s1r2nl_f64_sym_kernel<S1R2_SYM_VARIANTS[V].R, S1R2_SYM_VARIANTS[V].threads, F64_TJ, F64_STAGES,           \
+                                                S1R2_SYM_VARIANTS[V].minb, S1R2_SYM_VARIANTS[V].unroll, MM>;                        \
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                 \
+        kern<<<nb * pl.n_chunks, S1R2_SYM_VARIANTS[V].threads, smem, e->stream>>>(sa, k);                                           \
+    }
+#define LAUNCH_S1R2_SYM_V(V)                                   \
+    case V:                                                    \
+        if (k.M == 3) LAUNCH_S1R2_SYM_VM(V, 3)                 \
+        else if (k.M == 4) LAUNCH_S1R2_SYM_VM(V, 4)            \
+        else LAUNCH_S1R2_SYM_VM(V, 5)                          \
+        break;
+            switch (s1r2_sym_variant()) { LAUNCH_S1R2_SYM_V(0) LAUNCH_S1R2_SYM_V(1) LAUNCH_S1R2_SYM_V(2) LAUNCH_S1R2_SYM_V(3) }
+#undef LAUNCH_S1R2_SYM_V
+#undef LAUNCH_S1R2_SYM_VM
+        } else if (F64) {
             switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) LAUNCH_SYM(3) }
         } else {
             switch (sym32_variant()) { LAUNCH_SYM32(0) LAUNCH_SYM32(1) LAUNCH_SYM32(2) }
@@ -825,7 +883,16 @@ int forces_impl(steps_b200_engine *e, int id_min, int id_max) {
     Plan pl;
     const int n_i = id_max - id_min + 1;
     int rc;
-    if (sym_call(e, id_min, n_i)) rc = (e->real_bytes == 8) ? launch_pair_sym<double>(e, id_min, n_i, pl) : launch_pair_sym<float>(e, id_min, n_i, pl);
+    bool sym = sym_call(e, id_min, n_i);
+    if (sym && e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP) {
+        // the image-slot arithmetic needs every z inside [0, L) (pack kernel's flag; the same on every rank: all pack the full replica);
+        // otherwise this evaluation takes the one-sided launch, whose exact-branch arm handles any z
+        int zflag = 0;
+        CU_TRY(cudaMemcpyAsync(&zflag, e->d_zflag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        if (zflag != 0) sym = false;
+    }
+    if (sym) rc = (e->real_bytes == 8) ? launch_pair_sym<double>(e, id_min, n_i, pl) : launch_pair_sym<float>(e, id_min, n_i, pl);
     else rc = (e->real_bytes == 8) ? launch_pair<double>(e, id_min, n_i, pl) : launch_pair<float>(e, id_min, n_i, pl);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(e->ev[1], e->stream));
@@ -936,7 +1003,7 @@ extern "C" int steps_b200_engine_create(steps_b200_engine **out, const steps_b20
     for (auto &ev : e->ev) E_TRY(cudaEventCreate(&ev));
     for (auto &ev : e->marks) E_TRY(cudaEventCreate(&ev));
 #undef E_TRY
-    if (upload_tables(e) || setup_partition(e, real_bytes == 8 ? sym_env_default() : sym_f32_env_default())) {
+    if (upload_tables(e) || setup_partition(e, sym_default_for(e))) {
         steps_b200_engine_destroy(e);
         return 1;
     }
@@ -1042,7 +1109,7 @@ extern "C" int steps_b200_engine_comm_init(steps_b200_engine *e, const void *id1
     e->nranks = nranks;
     DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
-    if (setup_partition(e, e->sym || (e->real_bytes == 8 ? sym_env_default() : sym_f32_env_default()))) return 1;
+    if (setup_partition(e, e->sym || sym_default_for(e))) return 1;
     if (nranks == 1) return 0;
     if (nccl_load()) return 1;
     ncclUniqueId id;

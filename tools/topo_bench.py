@@ -67,7 +67,7 @@ def run(case):
         ms.append(eng.pair_kernel_ms())
     F = eng.download_forces(0, min(g.N, 8) - 1)
     best = min(ms[1:])
-    print(json.dumps({"case": case, "name": c.name, "N": int(g.N), "pair_kernel_ms": best, "force_ms": eng.timings()[0], "pairs_per_s": g.N * float(g.N) / (best * 1e-3),
+    print(json.dumps({"case": case, "sym": bool(eng.symmetric), "name": c.name, "N": int(g.N), "pair_kernel_ms": best, "force_ms": eng.timings()[0], "pairs_per_s": g.N * float(g.N) / (best * 1e-3),
                       "image_evals_per_pair": evals, "shape": eng.launch_shape(0, g.N - 1), "table_build_s": round(tb, 2), "F0": [float(v) for v in F[:3]]}), flush=True)
     eng.close()
 

@@ -2,8 +2,10 @@
 image loop, against the one-sided tuned kernel, for every image count, with softened pairs, pairs at the image cut, z outside
 the box (fallback), several passes and every rank of a multi-GPU job played on one GPU.
 
-EXPERIMENTAL: the kernel was written after round 1's GPU budget was spent and has not run on a GPU yet; it is opt-in in the
-library (STEPS_B200_S1R2_SYM=1 or Engine.set_symmetric(True)) and these tests run only with STEPS_B200_EXPERIMENTAL=1:
+EXPERIMENTAL: the kernel was written when round 1's GPU budget was almost spent: 12 of these tests (image counts, ragged sizes,
+multi-rank) passed on a B200 in the last seconds of it (profiles/r1ad_s1r2_sym_tests.log), the other four have not run yet.  The
+kernel is opt-in in the library (STEPS_B200_S1R2_SYM=1 or Engine.set_symmetric(True)) and these tests run only with
+STEPS_B200_EXPERIMENTAL=1:
     STEPS_B200_EXPERIMENTAL=1 python -m pytest tests/test_gpu_s1r2_sym.py -m gpu -q -s"""
 import ctypes as C
 import os
@@ -87,7 +89,8 @@ def test_s1r2_sym_ragged_sizes(n):
 
 
 def test_s1r2_sym_too_small_falls_back():
-    c = cylinder(700, 5)
+    # one i-block of 384 (the default shape): the engine keeps the one-sided kernel
+    c = ic.s1r2_cylinder(380, 24, 4, 5, lookup=False, is_periodic=2, L=L, r_sim=60.0, d_s=10.0, r_crit=15.0)
     Fo = reference_forces(c)
     F, used, _ = engine_forces(c, True)
     assert not used

@@ -7,6 +7,7 @@
 #include "pair_r3_sym.cuh"
 #include "pair_r3_sym_f32.cuh"
 #include "pair_s1r2_sym.cuh"
+#include "pair_generic_sym.cuh"
 
 namespace steps {
 

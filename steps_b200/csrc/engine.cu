@@ -430,7 +430,34 @@ bool s1r2_sym_env_default() {
     }
     return v == 1 && sym_env_default();
 }
+// Shapes of the action-reaction kernel of the table-lookup topologies (pair_generic_sym.cuh); STEPS_B200_GEN_SYM_VARIANT=k
+constexpr SymVariant GEN_SYM_VARIANTS[] = {
+    {2, 128, 3, 1},  // 0: i-block 256, <= 168 registers
+    {2, 128, 4, 1},  // 1: i-block 256, <= 128 registers (the one-sided kernel's budget)
+    {1, 128, 4, 1},  // 2: i-block 128
+};
+constexpr int N_GEN_SYM_VARIANTS = sizeof(GEN_SYM_VARIANTS) / sizeof(GEN_SYM_VARIANTS[0]);
+int gen_sym_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("STEPS_B200_GEN_SYM_VARIANT");
+        v = s ? atoi(s) : 0;
+        if (v < 0 || v >= N_GEN_SYM_VARIANTS) v = 0;
+    }
+    return v;
+}
+// OPT-IN (STEPS_B200_GEN_SYM=1 or an explicit steps_b200_engine_set_symmetric(e, 1)): not run on a GPU yet.
+bool gen_sym_env_default() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("STEPS_B200_GEN_SYM");
+        v = (s && atoi(s) != 0) ? 1 : 0;
+    }
+    return v == 1 && sym_env_default();
+}
+bool gen_sym_topology(const steps_b200_engine *e) { return e->p.topology == STEPS_TOPO_T3 || e->p.topology == STEPS_TOPO_S1R2_LOOKUP; }
 SymVariant sym_shape(const steps_b200_engine *e) {
+    if (gen_sym_topology(e)) return GEN_SYM_VARIANTS[gen_sym_variant()];
     if (e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP) return S1R2_SYM_VARIANTS[s1r2_sym_variant()];
     return e->real_bytes == 8 ? SYM_VARIANTS[sym_variant()] : SYM32_VARIANTS[sym32_variant()];
 }
@@ -438,6 +465,7 @@ SymVariant sym_shape(const steps_b200_engine *e) {
 bool sym_default_for(const steps_b200_engine *e) {
     if (e->p.topology == STEPS_TOPO_R3) return e->real_bytes == 8 ? sym_env_default() : sym_f32_env_default();
     if (tuned_s1r2(e)) return s1r2_sym_env_default();
+    if (gen_sym_topology(e)) return gen_sym_env_default();
     return false;
 }
 
@@ -516,7 +544,7 @@ int setup_partition(steps_b200_engine *e, bool want_sym) {
     e->sym = false;
     e->h_rules.clear();
     steps_b200_partition(e->n, e->nranks, e->rank, &e->i_lo, &e->i_hi);
-    if (!want_sym || !(e->p.topology == STEPS_TOPO_R3 || tuned_s1r2(e))) return 0;
+    if (!want_sym || !(e->p.topology == STEPS_TOPO_R3 || tuned_s1r2(e) || gen_sym_topology(e))) return 0;
     const SymVariant sv = sym_shape(e);
     const int ib = sv.R * sv.threads;
     int lo, hi;
@@ -810,7 +838,24 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
         kern<<<nb * pl.n_chunks, SYM32_VARIANTS[K].threads, smem, e->stream>>>(sa);                                    \
     } break;
-        if (F64 && e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP) {
+        if (gen_sym_topology(e)) {
+            const size_t smem_gen = (size_t)GEN_STAGES * GEN_TJ * sizeof(JRec) + (size_t)2 * nwarps * 3 * GEN_TJ * sizeof(T) + 2 * GEN_STAGES * sizeof(uint64_t);
+#define LAUNCH_GEN_SYM_VT(V, TOPO)                                                                                                  \
+    {                                                                                                                               \
+        auto kern = force_generic_sym_kernel<T, TOPO, GEN_SYM_VARIANTS[V].R, GEN_SYM_VARIANTS[V].threads, GEN_TJ, GEN_STAGES,       \
+                                             GEN_SYM_VARIANTS[V].minb>;                                                             \
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gen));                             \
+        kern<<<nb * pl.n_chunks, GEN_SYM_VARIANTS[V].threads, smem_gen, e->stream>>>(sa, e->tp);                                    \
+    }
+#define LAUNCH_GEN_SYM_V(V)                                                   \
+    case V:                                                                   \
+        if (e->p.topology == STEPS_TOPO_T3) LAUNCH_GEN_SYM_VT(V, 1)           \
+        else LAUNCH_GEN_SYM_VT(V, 2)                                          \
+        break;
+            switch (gen_sym_variant()) { LAUNCH_GEN_SYM_V(0) LAUNCH_GEN_SYM_V(1) LAUNCH_GEN_SYM_V(2) }
+#undef LAUNCH_GEN_SYM_V
+#undef LAUNCH_GEN_SYM_VT
+        } else if (F64 && e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP) {
             S1R2Consts k{};
             k.L = e->tp.L;
             k.cut = e->tp.ewald_cut * e->tp.L;

@@ -1,0 +1,222 @@
+// pair_generic_sym.cuh -- action-reaction evaluation for the table-lookup topologies: T^3 (nearest image + tricubic Ewald
+// correction, forces_cuda.cu:567-645) and the S^1xR^2 lookup build (forces_cuda.cu:764-864), both precisions.
+// OPT-IN (STEPS_B200_GEN_SYM=1 or steps_b200_engine_set_symmetric(e, 1)): written after round 1's GPU budget was spent; it has
+// not run on a GPU yet (tests/test_gpu_generic_sym.py, gated by STEPS_B200_EXPERIMENTAL=1).
+//
+// The pair term of these topologies is  F_i += m_j t(d),  t(d) = w(|d|, s_i+s_j) d - D(d),  d = nearest image of x_j - x_i.
+// w is even in d and the interpolated correction D is odd (the tables are built from inversion-symmetric image sums and the
+// Catmull-Rom / TSC / CIC weights are mirror symmetric; in floating point D(-d) = -D(d) holds to the rounding of the cell
+// coordinate, ~1e-15 of D), so one evaluation of t -- the 64-point gather is the cost of this path -- serves both particles:
+//     F_i += m_j t,   F_j -= m_i t.
+// Scheme, rules, passes and reductions are those of pair_r3_sym.cuh; the per-pair arithmetic is that of pair_exact()
+// (pair_generic.cuh), operation by operation, with the mass factored out.
+#pragma once
+#include "pair_generic.cuh"
+#include "pair_r3_sym.cuh"
+
+namespace steps {
+
+// unit-mass pair vector t of pair_exact<T, TOPO>: F_i += m_j t
+template <typename T, int TOPO>
+__device__ __forceinline__ void pair_exact_unit(const TopoParams &tp, T xi, T yi, T zi, T si, T xj, T yj, T zj, T sj, T &tx, T &ty, T &tz) {
+    static_assert(TOPO == 1 || TOPO == 2, "table-lookup topologies");
+    const T beta = si + sj;
+    T dx = xj - xi, dy = yj - yi, dz = zj - zi;
+    const T L = (T)tp.L;
+    if (TOPO == 1) {
+        if (fabs(dx) > (T)0.5 * L) dx = dx - L * dx / fabs(dx);
+        if (fabs(dy) > (T)0.5 * L) dy = dy - L * dy / fabs(dy);
+        if (fabs(dz) > (T)0.5 * L) dz = dz - L * dz / fabs(dz);
+        const T r = sqrt(dx * dx + dy * dy + dz * dz);
+        const T w = softened_w<T>(r, beta);
+        if (tp.is_periodic == 1) {
+            tx = w * dx; ty = w * dy; tz = w * dz;
+        } else {
+            T D[3];
+            t3_interpolate<T>(tp.dim0, L, static_cast<const T *>(tp.table), dx, dy, dz, D);
+            tx = w * dx - D[0];
+            ty = w * dy - D[1];
+            tz = w * dz - D[2];
+        }
+    } else {
+        if (dz > (T)0.5 * L) dz -= L;
+        else if (dz < (T)(-0.5) * L) dz += L;
+        const T r = sqrt(dx * dx + dy * dy + dz * dz);
+        const T w = softened_w<T>(r, beta);
+        if (tp.is_periodic >= 2) {
+            T D[3];
+            s1r2_interpolate<T>(tp, dx, dy, dz, D);
+            tx = w * dx - D[0];
+            ty = w * dy - D[1];
+            tz = w * dz - D[2];
+        } else {
+            tx = w * dx; ty = w * dy; tz = w * dz;
+        }
+    }
+}
+
+template <typename T, int TOPO, int R, int THREADS, int TJ, int STAGES, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const SymLaunchArgs sa, const TopoParams tp) {
+    using JRec = typename JRecOf<T>::type;
+    constexpr int NWARPS = THREADS / 32;
+    constexpr int IB = THREADS * R;
+    static_assert(THREADS >= TJ && TJ % 32 == 0 && IB % TJ == 0, "shape");
+    const R3LaunchArgs &a = sa.a;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    JRec *tiles = reinterpret_cast<JRec *>(smem_raw);
+    T *slots = reinterpret_cast<T *>(smem_raw + (size_t)STAGES * TJ * sizeof(JRec));  // [2][NWARPS][3][TJ]
+    uint64_t *full = reinterpret_cast<uint64_t *>(slots + 2 * NWARPS * 3 * TJ);
+    uint64_t *empty = full + STAGES;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int jc = blockIdx.x / a.n_ib;
+    const int gb = blockIdx.x - jc * a.n_ib;
+    const int ib = sa.b0 + gb;
+    const SymRule *__restrict__ rule = sa.rules + ib;
+    int ta, tb;
+    {
+        const int c0 = jc * a.tiles_per_chunk;
+        const int c1 = min(c0 + a.tiles_per_chunk, a.n_tiles);
+        ta = 0x7fffffff;
+        tb = -1;
+        {
+            const int lo = max(rule->diag_lo, c0), hi = min(rule->diag_hi, c1);
+            if (lo < hi) { ta = min(ta, lo); tb = max(tb, hi); }
+        }
+        for (int q = 0; q < rule->n_sym; ++q) {
+            const int lo = max(rule->sym_lo[q], c0), hi = min(rule->sym_hi[q], c1);
+            if (lo < hi) { ta = min(ta, lo); tb = max(tb, hi); }
+        }
+    }
+    T *__restrict__ fp = static_cast<T *>(a.fpart) + (size_t)jc * 3 * a.fstride;
+    if (tb <= ta) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int il = ib * IB + r * THREADS + tid;
+            if (il < a.n_i) {
+                fp[il] = 0;
+                fp[a.fstride + il] = 0;
+                fp[2 * (size_t)a.fstride + il] = 0;
+            }
+        }
+        return;
+    }
+    const int t0 = ta, nt = tb - ta;
+    const JRec *__restrict__ jrec = static_cast<const JRec *>(a.jrec);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NWARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int npre = nt < STAGES ? nt : STAGES;
+        for (int t = 0; t < npre; ++t) {
+            mbar_arrive_expect_tx(&full[t], TJ * sizeof(JRec));
+            tma_load_1d(tiles + (size_t)t * TJ, jrec + (size_t)(t0 + t) * TJ, TJ * sizeof(JRec), &full[t]);
+        }
+    }
+
+    T xi[R], yi[R], zi[R], si[R], mi[R], ax[R], ay[R], az[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int il0 = ib * IB + r * THREADS + tid;
+        const int il = il0 < a.n_i ? il0 : a.n_i - 1;
+        const JRec me = jrec[a.id_min + il];
+        xi[r] = me.x; yi[r] = me.y; zi[r] = me.z; si[r] = me.s;
+        mi[r] = il0 < a.n_i ? (T)me.m : (T)0;  // a clamped duplicate must not act on the j side
+        ax[r] = ay[r] = az[r] = 0;
+    }
+    int nsym = 0;
+
+    for (int t = 0; t < nt; ++t) {
+        const int s = t % STAGES;
+        const uint32_t ph = (uint32_t)(t / STAGES) & 1u;
+        if (tid == 0 && t >= 1 && (t - 1 + STAGES) < nt) {
+            const int sp = (t - 1) % STAGES;
+            const uint32_t php = (uint32_t)((t - 1) / STAGES) & 1u;
+            mbar_wait(&empty[sp], php);
+            mbar_arrive_expect_tx(&full[sp], TJ * sizeof(JRec));
+            tma_load_1d(tiles + (size_t)sp * TJ, jrec + (size_t)(t0 + t - 1 + STAGES) * TJ, TJ * sizeof(JRec), &full[sp]);
+        }
+        mbar_wait(&full[s], ph);
+        const JRec *__restrict__ Tl = tiles + (size_t)s * TJ;
+        const int cls = sym_tile_class(*rule, t0 + t);  // CTA-uniform
+        // the last tile is padded with massless far-away records: they are never evaluated (periodic wraps and table
+        // lookups must not see the padding coordinates)
+        const int jn = min(TJ, a.n_j - (t0 + t) * TJ);
+        if (cls == 1) {
+            // ---- the i-block's own tiles: one-sided, exactly the loop of force_generic_kernel ----
+            for (int jj = 0; jj < jn; ++jj) {
+                const JRec q = Tl[jj];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    pair_exact<T, TOPO>(tp, xi[r], yi[r], zi[r], si[r], (T)q.x, (T)q.y, (T)q.z, (T)q.m, (T)q.s, ax[r], ay[r], az[r]);
+            }
+        } else if (cls == 2) {
+            // ---- symmetric tile: the 32 records of a group visit the lanes systolically (pair_r3_sym.cuh) ----
+            T *__restrict__ slot = slots + ((size_t)(nsym & 1) * NWARPS + warp) * 3 * TJ;
+            for (int g0 = 0; g0 < TJ; g0 += 32) {
+                T vx = 0, vy = 0, vz = 0;
+#pragma unroll 1
+                for (int s2 = 0; s2 < 32; ++s2) {
+                    const int jidx = g0 + ((lane + s2) & 31);
+                    if (jidx < jn) {
+                        const JRec q = Tl[jidx];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            T tx, ty, tz;
+                            pair_exact_unit<T, TOPO>(tp, xi[r], yi[r], zi[r], si[r], (T)q.x, (T)q.y, (T)q.z, (T)q.s, tx, ty, tz);
+                            const T mj = (T)q.m;
+                            ax[r] += mj * tx;
+                            ay[r] += mj * ty;
+                            az[r] += mj * tz;
+                            vx += mi[r] * tx;
+                            vy += mi[r] * ty;
+                            vz += mi[r] * tz;
+                        }
+                    }
+                    __syncwarp();
+                    // the accumulator follows its record: lane l takes over the record lane l+1 just worked on
+                    vx = __shfl_sync(0xffffffffu, vx, (lane + 1) & 31);
+                    vy = __shfl_sync(0xffffffffu, vy, (lane + 1) & 31);
+                    vz = __shfl_sync(0xffffffffu, vz, (lane + 1) & 31);
+                }
+                slot[g0 + lane] = vx;
+                slot[TJ + g0 + lane] = vy;
+                slot[2 * TJ + g0 + lane] = vz;
+            }
+            __syncthreads();
+            if (tid < TJ) {
+                const T *__restrict__ sb = slots + (size_t)(nsym & 1) * NWARPS * 3 * TJ;
+                T *__restrict__ gp = static_cast<T *>(sa.gpart) + (size_t)gb * 3 * sa.n_pad + (size_t)(t0 + t) * TJ + tid;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    T v = 0;
+#pragma unroll
+                    for (int w = 0; w < NWARPS; ++w) v += sb[((size_t)w * 3 + c) * TJ + tid];
+                    gp[(size_t)c * sa.n_pad] = v;
+                }
+            }
+            ++nsym;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int il = ib * IB + r * THREADS + tid;
+        if (il < a.n_i) {
+            fp[il] = ax[r];
+            fp[a.fstride + il] = ay[r];
+            fp[2 * (size_t)a.fstride + il] = az[r];
+        }
+    }
+}
+
+}  // namespace steps

@@ -230,6 +230,7 @@ struct steps_b200_engine {
     SymRule *d_rules = nullptr;
     void *d_gpart = nullptr, *d_fsym = nullptr;  // REAL of the build
     size_t gpart_bytes = 0;
+    Plan last_sym_plan{};        // plan of the last action-reaction evaluation (the debug hook redoes its final reduction)
 };
 
 namespace {
@@ -590,7 +591,19 @@ Plan sym_plan(const steps_b200_engine *e, int n_i) {
     p.n_tiles = e->n_tiles;
     p.slots = e->num_sms * sv.minb;
     int target = SYM_TARGET_CHUNKS;
-    if (const char *s = getenv("STEPS_B200_SYM_CHUNKS")) target = std::max(1, atoi(s));  // tuning knob
+    if (const char *s = getenv("STEPS_B200_SYM_CHUNKS")) {
+        target = std::max(1, atoi(s));  // tuning knob
+    } else if (p.n_tiles >= 4096) {
+        // Large N: only a few j-side rows fit the row buffer, a pass then has few CTAs and its last wave runs mostly empty
+        // (modelled with list scheduling of the CTA costs: 0.88 of the ideal at C5, N = 16.7M FP32, 79 rows per pass).  Shorter
+        // chunks restore >= 24 waves of CTAs per pass (0.96).  Nothing changes while rows x 56 >= 24 x slots: C2 and every
+        // configuration measured in round 1 keep their 56 chunks.
+        const size_t row_bytes = (size_t)3 * e->n_pad * e->real_bytes;
+        size_t rows = e->gpart_bytes ? e->gpart_bytes / row_bytes : std::max<size_t>(1, ((size_t)16 << 30) / row_bytes);
+        rows = std::max<size_t>(1, std::min<size_t>(rows, (size_t)p.n_ib));
+        const size_t want = (size_t)24 * p.slots;
+        if (rows * (size_t)target < want) target = (int)std::min<size_t>(160, (want + rows - 1) / rows);
+    }
     p.tiles_per_chunk = std::max(MIN_TILES_PER_CHUNK, (p.n_tiles + target - 1) / target);
     p.n_chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
     p.ctas = p.n_ib * p.n_chunks;
@@ -762,17 +775,9 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     using JRec = typename JRecOf<T>::type;
     constexpr bool F64 = sizeof(T) == 8;
     const SymVariant sv = sym_shape(e);
-    const Plan pl = sym_plan(e, n_i);
-    plan_out = pl;
-    if ((int)e->h_rules.size() != pl.n_ib) return fail("symmetric path: rule table does not match the i-range");
-    const size_t need = (size_t)pl.n_chunks * 3 * (size_t)n_i * sizeof(T);
-    if (need > e->fpart_bytes) {
-        if (e->d_fpart) CU_TRY(cudaFree(e->d_fpart));
-        e->d_fpart = nullptr;
-        e->fpart_bytes = 0;
-        CU_TRY(cudaMalloc(&e->d_fpart, need));
-        e->fpart_bytes = need;
-    }
+    const int n_ib_call = (n_i + sv.R * sv.threads - 1) / (sv.R * sv.threads);
+    if ((int)e->h_rules.size() != n_ib_call) return fail("symmetric path: rule table does not match the i-range");
+    // the j-side row buffer first: the plan below looks at how many rows a pass holds
     const size_t row_bytes = (size_t)3 * e->n_pad * sizeof(T);
     if (!e->d_fsym) CU_TRY(cudaMalloc(&e->d_fsym, row_bytes));
     if (!e->d_gpart) {
@@ -781,7 +786,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         size_t budget = std::min((size_t)16 << 30, free_b / 3);
         if (const char *s = getenv("STEPS_B200_SYM_GPART_MB")) budget = (size_t)atoll(s) << 20;
         size_t rows = std::max<size_t>(1, budget / row_bytes);
-        rows = std::min<size_t>(rows, (size_t)pl.n_ib);
+        rows = std::min<size_t>(rows, (size_t)n_ib_call);
         // a smaller buffer only means more passes: halve until the allocation succeeds
         cudaError_t err = cudaErrorMemoryAllocation;
         while (rows >= 1) {
@@ -796,6 +801,17 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         e->gpart_bytes = rows * row_bytes;
     }
     const int rows = (int)(e->gpart_bytes / row_bytes);
+    const Plan pl = sym_plan(e, n_i);
+    plan_out = pl;
+    e->last_sym_plan = pl;
+    const size_t need = (size_t)pl.n_chunks * 3 * (size_t)n_i * sizeof(T);
+    if (need > e->fpart_bytes) {
+        if (e->d_fpart) CU_TRY(cudaFree(e->d_fpart));
+        e->d_fpart = nullptr;
+        e->fpart_bytes = 0;
+        CU_TRY(cudaMalloc(&e->d_fpart, need));
+        e->fpart_bytes = need;
+    }
     CU_TRY(cudaMemsetAsync(e->d_fsym, 0, row_bytes, e->stream));
     SymLaunchArgs sa{};
     sa.a.jrec = e->d_jrec;
@@ -1132,7 +1148,7 @@ extern "C" int steps_b200_engine_debug_fsym(steps_b200_engine *e, void *fsym_out
     if (fsym_in) {
         CU_TRY(cudaMemcpyAsync(e->d_fsym, fsym_in, bytes, cudaMemcpyHostToDevice, e->stream));
         const int n_i = e->i_hi - e->i_lo;
-        if (finish_pair_sym(e, e->i_lo, n_i, sym_plan(e, n_i))) return 1;
+        if (finish_pair_sym(e, e->i_lo, n_i, e->last_sym_plan)) return 1;
         CU_TRY(cudaStreamSynchronize(e->stream));
     }
     return 0;

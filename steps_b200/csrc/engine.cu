@@ -432,10 +432,15 @@ bool s1r2_sym_env_default() {
     return v == 1 && sym_env_default();
 }
 // Shapes of the action-reaction kernel of the table-lookup topologies (pair_generic_sym.cuh); STEPS_B200_GEN_SYM_VARIANT=k
+// (the `unroll` field selects the arithmetic here: 0 = the reference's operations one by one, 1 = the lean T^3 sequence of
+// pair_t3_fast_unit; the S^1xR^2 lookup build always runs the exact one)
 constexpr SymVariant GEN_SYM_VARIANTS[] = {
-    {2, 128, 3, 1},  // 0: i-block 256, <= 168 registers
-    {2, 128, 4, 1},  // 1: i-block 256, <= 128 registers (the one-sided kernel's budget)
-    {1, 128, 4, 1},  // 2: i-block 128
+    {2, 128, 3, 0},  // 0: i-block 256, <= 168 registers
+    {2, 128, 4, 0},  // 1: i-block 256, <= 128 registers (the one-sided kernel's budget)
+    {1, 128, 4, 0},  // 2: i-block 128
+    {2, 128, 3, 1},  // 3: shape 0, lean T^3 arithmetic
+    {2, 128, 4, 1},  // 4: shape 1, lean T^3 arithmetic
+    {3, 128, 2, 1},  // 5: i-block 384, <= 255 registers, lean T^3 arithmetic
 };
 constexpr int N_GEN_SYM_VARIANTS = sizeof(GEN_SYM_VARIANTS) / sizeof(GEN_SYM_VARIANTS[0]);
 int gen_sym_variant() {
@@ -856,19 +861,20 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     } break;
         if (gen_sym_topology(e)) {
             const size_t smem_gen = (size_t)GEN_STAGES * GEN_TJ * sizeof(JRec) + (size_t)2 * nwarps * 3 * GEN_TJ * sizeof(T) + 2 * GEN_STAGES * sizeof(uint64_t);
-#define LAUNCH_GEN_SYM_VT(V, TOPO)                                                                                                  \
+#define LAUNCH_GEN_SYM_VT(V, TOPO, FASTV)                                                                                                \
     {                                                                                                                               \
         auto kern = force_generic_sym_kernel<T, TOPO, GEN_SYM_VARIANTS[V].R, GEN_SYM_VARIANTS[V].threads, GEN_TJ, GEN_STAGES,       \
-                                             GEN_SYM_VARIANTS[V].minb>;                                                             \
+                                             GEN_SYM_VARIANTS[V].minb, FASTV>;                                                      \
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gen));                             \
         kern<<<nb * pl.n_chunks, GEN_SYM_VARIANTS[V].threads, smem_gen, e->stream>>>(sa, e->tp);                                    \
     }
 #define LAUNCH_GEN_SYM_V(V)                                                   \
     case V:                                                                   \
-        if (e->p.topology == STEPS_TOPO_T3) LAUNCH_GEN_SYM_VT(V, 1)           \
-        else LAUNCH_GEN_SYM_VT(V, 2)                                          \
+        if (e->p.topology == STEPS_TOPO_T3 && GEN_SYM_VARIANTS[V].unroll == 1 && e->p.is_periodic >= 2) LAUNCH_GEN_SYM_VT(V, 1, true) \
+        else if (e->p.topology == STEPS_TOPO_T3) LAUNCH_GEN_SYM_VT(V, 1, false) \
+        else LAUNCH_GEN_SYM_VT(V, 2, false)                                   \
         break;
-            switch (gen_sym_variant()) { LAUNCH_GEN_SYM_V(0) LAUNCH_GEN_SYM_V(1) LAUNCH_GEN_SYM_V(2) }
+            switch (gen_sym_variant()) { LAUNCH_GEN_SYM_V(0) LAUNCH_GEN_SYM_V(1) LAUNCH_GEN_SYM_V(2) LAUNCH_GEN_SYM_V(3) LAUNCH_GEN_SYM_V(4) LAUNCH_GEN_SYM_V(5) }
 #undef LAUNCH_GEN_SYM_V
 #undef LAUNCH_GEN_SYM_VT
         } else if (F64 && e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP) {

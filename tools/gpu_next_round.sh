@@ -22,9 +22,12 @@ cut -c1-300 $O/${TAG}_s1r2_sweep.txt
 stamp "table-lookup topologies (T^3, S^1xR^2 lookup): action-reaction kernel tests"
 STEPS_B200_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_generic_sym.py -m gpu -q -s --timeout 120 > $O/${TAG}_generic_sym_tests.log 2>&1
 echo "rc=$?" >> $O/${TAG}_generic_sym_tests.log; grep -E " sym|passed|failed|rc=|Error|assert" $O/${TAG}_generic_sym_tests.log | cut -c1-260 | tail -20
+stamp "same tests with the lean T^3 arithmetic (shape 3)"
+STEPS_B200_EXPERIMENTAL=1 STEPS_B200_GEN_SYM_VARIANT=3 timeout 300 python -m pytest tests/test_gpu_generic_sym.py -m gpu -q -s --timeout 120 -k "t3 or multi_rank or softened or deterministic or kdk" > $O/${TAG}_generic_sym_tests_lean.log 2>&1
+echo "rc=$?" >> $O/${TAG}_generic_sym_tests_lean.log; grep -E " sym|passed|failed|rc=|Error|assert" $O/${TAG}_generic_sym_tests_lean.log | cut -c1-260 | tail -20
 stamp "T^3 64^3 and S^1xR^2 lookup N=200k: one-sided, then the action-reaction shapes"
 timeout 200 python tools/topo_bench.py t3:64,s1r2:200000 > $O/${TAG}_generic_sweep.txt 2>&1
-for v in 0 1 2; do
+for v in 0 1 2 3 4 5; do
   STEPS_B200_GEN_SYM=1 STEPS_B200_GEN_SYM_VARIANT=$v timeout 200 python tools/topo_bench.py t3:64,s1r2:200000 >> $O/${TAG}_generic_sweep.txt 2>&1
 done
 cut -c1-300 $O/${TAG}_generic_sweep.txt

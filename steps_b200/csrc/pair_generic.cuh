@@ -11,6 +11,16 @@
 
 namespace steps {
 
+// read-only table load: LDG.CI on the device; a plain load when the CPU test tier runs these functions on the host (tests/hostcheck)
+template <typename T>
+__host__ __device__ __forceinline__ T table_ld(const T *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
 template <typename T> struct JRecOf;
 template <> struct JRecOf<double> { using type = JRec64; };
 template <> struct JRecOf<float> { using type = JRec32; };
@@ -31,13 +41,13 @@ struct TopoParams {
 };
 
 // ---------------------------------------------------------------- T^3 tricubic (forces_cuda.cu:87-167)
-__device__ __forceinline__ int imodp(int i, int n) {
+__host__ __device__ __forceinline__ int imodp(int i, int n) {
     int r = i % n;
     return (r < 0) ? (r + n) : r;
 }
 
 template <typename T>
-__device__ __forceinline__ void map_to_centered_grid(T r, T L, int Ngrid, int &i0, T &fx) {
+__host__ __device__ __forceinline__ void map_to_centered_grid(T r, T L, int Ngrid, int &i0, T &fx) {
     const T grid_spacing = L / (T)Ngrid;
     const T u = (r + L * (T)0.5) / grid_spacing - (T)0.5;
     const T uf = floor(u);
@@ -46,7 +56,7 @@ __device__ __forceinline__ void map_to_centered_grid(T r, T L, int Ngrid, int &i
 }
 
 template <typename T>
-__device__ __forceinline__ void cubic_weights(T t, T w[4]) {
+__host__ __device__ __forceinline__ void cubic_weights(T t, T w[4]) {
     const T t2 = t * t;
     const T t3 = t * t2;
     w[0] = (T)(-0.5) * t3 + t2 - (T)0.5 * t;
@@ -56,7 +66,7 @@ __device__ __forceinline__ void cubic_weights(T t, T w[4]) {
 }
 
 template <typename T>
-__device__ __forceinline__ void t3_interpolate(int Ngrid, T L, const T *__restrict__ table, T dx, T dy, T dz, T D[3]) {
+__host__ __device__ __forceinline__ void t3_interpolate(int Ngrid, T L, const T *__restrict__ table, T dx, T dy, T dz, T D[3]) {
     int ix0, iy0, iz0;
     T fx, fy, fz;
     map_to_centered_grid(dx, L, Ngrid, ix0, fx);
@@ -82,9 +92,9 @@ __device__ __forceinline__ void t3_interpolate(int Ngrid, T L, const T *__restri
             for (int k = 0; k < 4; ++k) {
                 const T w_xyz = w_xy * wz[k];
                 const T *__restrict__ e = table + (row + izs[k]) * 3u;
-                s0 += w_xyz * __ldg(e + 0);
-                s1 += w_xyz * __ldg(e + 1);
-                s2 += w_xyz * __ldg(e + 2);
+                s0 += w_xyz * table_ld(e + 0);
+                s1 += w_xyz * table_ld(e + 1);
+                s2 += w_xyz * table_ld(e + 2);
             }
         }
     }
@@ -93,7 +103,7 @@ __device__ __forceinline__ void t3_interpolate(int Ngrid, T L, const T *__restri
 
 // ---------------------------------------------------------------- S^1xR^2 (rho,z) table (forces_cuda.cu:176-455)
 template <typename T>
-__device__ __forceinline__ void s1r2_ngp(const T *__restrict__ Tb, int Nrho, int Nz, T rho_max, T Lz, T rho, T z, T D[2]) {
+__host__ __device__ __forceinline__ void s1r2_ngp(const T *__restrict__ Tb, int Nrho, int Nz, T rho_max, T Lz, T rho, T z, T D[2]) {
     T rc = rho;
     if (rho < (T)0) rc = (T)0;
     if (rho > rho_max) rc = rho_max;
@@ -108,12 +118,12 @@ __device__ __forceinline__ void s1r2_ngp(const T *__restrict__ Tb, int Nrho, int
     if (ir > Nrho - 1) ir = Nrho - 1;
     iz = imodp(iz, Nz);
     const size_t base = (size_t)ir * (size_t)Nz * 2u + (size_t)iz * 2u;
-    D[0] = __ldg(Tb + base);
-    D[1] = __ldg(Tb + base + 1);
+    D[0] = table_ld(Tb + base);
+    D[1] = table_ld(Tb + base + 1);
 }
 
 template <typename T>
-__device__ __forceinline__ void s1r2_cic(const T *__restrict__ Tb, int Nrho, int Nz, T rho_max, T Lz, T rho, T z, T D[2]) {
+__host__ __device__ __forceinline__ void s1r2_cic(const T *__restrict__ Tb, int Nrho, int Nz, T rho_max, T Lz, T rho, T z, T D[2]) {
     T ur;
     const T drho = rho_max / (T)max(1, Nrho - 1);
     if (rho < (T)0) ur = 0;
@@ -135,13 +145,13 @@ __device__ __forceinline__ void s1r2_cic(const T *__restrict__ Tb, int Nrho, int
     T w10 = fr; w10 *= ((T)1 - fz);
     T w01 = (T)1 - fr; w01 *= fz;
     const T w11 = fr * fz;
-    auto get = [&](int ir, int iz, int c) -> T { return __ldg(Tb + ((size_t)ir * (size_t)Nz + (size_t)iz) * 2u + c); };
+    auto get = [&](int ir, int iz, int c) -> T { return table_ld(Tb + ((size_t)ir * (size_t)Nz + (size_t)iz) * 2u + c); };
     D[0] = w00 * get(ir0, iz0, 0) + w10 * get(ir1, iz0, 0) + w01 * get(ir0, iz1, 0) + w11 * get(ir1, iz1, 0);
     D[1] = w00 * get(ir0, iz0, 1) + w10 * get(ir1, iz0, 1) + w01 * get(ir0, iz1, 1) + w11 * get(ir1, iz1, 1);
 }
 
 template <typename T>
-__device__ __forceinline__ void s1r2_tsc(const T *__restrict__ Tb, int Nrho, int Nz, T rho_max, T Lz, T rho, T z, T D[2]) {
+__host__ __device__ __forceinline__ void s1r2_tsc(const T *__restrict__ Tb, int Nrho, int Nz, T rho_max, T Lz, T rho, T z, T D[2]) {
     T ur;
     const T drho = rho_max / (T)max(1, Nrho - 1);
     if (rho < (T)0) ur = (T)0;
@@ -169,14 +179,14 @@ __device__ __forceinline__ void s1r2_tsc(const T *__restrict__ Tb, int Nrho, int
         const T wz = wzv[q];
         const T wr0 = wrm * wz, wr1 = wrc * wz, wr2 = wrp * wz;
         const size_t c = (size_t)izv[q] * 2u;
-        d0 += wr0 * __ldg(Tb + b0 + c) + wr1 * __ldg(Tb + b1 + c) + wr2 * __ldg(Tb + b2 + c);
-        d1 += wr0 * __ldg(Tb + b0 + c + 1) + wr1 * __ldg(Tb + b1 + c + 1) + wr2 * __ldg(Tb + b2 + c + 1);
+        d0 += wr0 * table_ld(Tb + b0 + c) + wr1 * table_ld(Tb + b1 + c) + wr2 * table_ld(Tb + b2 + c);
+        d1 += wr0 * table_ld(Tb + b0 + c + 1) + wr1 * table_ld(Tb + b1 + c + 1) + wr2 * table_ld(Tb + b2 + c + 1);
     }
     D[0] = d0; D[1] = d1;
 }
 
 template <typename T>
-__device__ __forceinline__ void s1r2_interpolate(const TopoParams &tp, T dx, T dy, T dz, T D[3]) {
+__host__ __device__ __forceinline__ void s1r2_interpolate(const TopoParams &tp, T dx, T dy, T dz, T D[3]) {
     const T *__restrict__ Tb = static_cast<const T *>(tp.table);
     const T rho = sqrt(dx * dx + dy * dy);
     T Drz[2];
@@ -192,7 +202,7 @@ __device__ __forceinline__ void s1r2_interpolate(const TopoParams &tp, T dx, T d
 
 // ---------------------------------------------------------------- one (i,j) pair, exact reference arithmetic
 template <typename T, int TOPO>
-__device__ __forceinline__ void pair_exact(const TopoParams &tp, T xi, T yi, T zi, T si, T xj, T yj, T zj, T mj, T sj, T &ax,
+__host__ __device__ __forceinline__ void pair_exact(const TopoParams &tp, T xi, T yi, T zi, T si, T xj, T yj, T zj, T mj, T sj, T &ax,
                                            T &ay, T &az) {
     const T beta = si + sj;
     T dx = xj - xi, dy = yj - yi, dz = zj - zi;

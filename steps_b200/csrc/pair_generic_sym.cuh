@@ -18,7 +18,7 @@ namespace steps {
 
 // unit-mass pair vector t of pair_exact<T, TOPO>: F_i += m_j t
 template <typename T, int TOPO>
-__device__ __forceinline__ void pair_exact_unit(const TopoParams &tp, T xi, T yi, T zi, T si, T xj, T yj, T zj, T sj, T &tx, T &ty, T &tz) {
+__host__ __device__ __forceinline__ void pair_exact_unit(const TopoParams &tp, T xi, T yi, T zi, T si, T xj, T yj, T zj, T sj, T &tx, T &ty, T &tz) {
     static_assert(TOPO == 1 || TOPO == 2, "table-lookup topologies");
     const T beta = si + sj;
     T dx = xj - xi, dy = yj - yi, dz = zj - zi;
@@ -69,7 +69,7 @@ struct T3Fast {
 };
 
 template <typename T>
-__device__ __forceinline__ void t3_fast_axis(T d, T halfL, T inv_h, int N, int (&idx)[4], T (&w)[4]) {
+__host__ __device__ __forceinline__ void t3_fast_axis(T d, T halfL, T inv_h, int N, int (&idx)[4], T (&w)[4]) {
     const T u = (d + halfL) * inv_h - (T)0.5;
     const T uf = floor(u);
     int i0 = (int)uf;
@@ -87,7 +87,7 @@ __device__ __forceinline__ void t3_fast_axis(T d, T halfL, T inv_h, int N, int (
 }
 
 template <typename T>
-__device__ __forceinline__ void pair_t3_fast_unit(const T3Fast &k, const T *__restrict__ table, T xi, T yi, T zi, T si, T xj, T yj, T zj, T sj,
+__host__ __device__ __forceinline__ void pair_t3_fast_unit(const T3Fast &k, const T *__restrict__ table, T xi, T yi, T zi, T si, T xj, T yj, T zj, T sj,
                                                   T &tx, T &ty, T &tz) {
     const T L = (T)k.L, halfL = (T)k.halfL, inv_h = (T)k.inv_h;
     const int N = k.N;
@@ -122,14 +122,14 @@ __device__ __forceinline__ void pair_t3_fast_unit(const T3Fast &k, const T *__re
             T p0, p1, p2;
             {
                 const T *__restrict__ e = row + zo[0];
-                p0 = wz[0] * __ldg(e); p1 = wz[0] * __ldg(e + 1); p2 = wz[0] * __ldg(e + 2);
+                p0 = wz[0] * table_ld(e); p1 = wz[0] * table_ld(e + 1); p2 = wz[0] * table_ld(e + 2);
             }
 #pragma unroll
             for (int c = 1; c < 4; ++c) {
                 const T *__restrict__ e = row + zo[c];
-                p0 = fma(wz[c], __ldg(e), p0);
-                p1 = fma(wz[c], __ldg(e + 1), p1);
-                p2 = fma(wz[c], __ldg(e + 2), p2);
+                p0 = fma(wz[c], table_ld(e), p0);
+                p1 = fma(wz[c], table_ld(e + 1), p1);
+                p2 = fma(wz[c], table_ld(e + 2), p2);
             }
             const T wxy = wx[a] * wy[b];
             s0 = fma(wxy, p0, s0);

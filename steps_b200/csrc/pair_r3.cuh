@@ -53,7 +53,7 @@ static_assert(sizeof(JRec32) == 32, "JRec32 layout");
 // Exact softened kernel, branch structure and operation order of force_softening_cuda
 // (forces_cuda.cu:466-519).  Returns w (without the mass factor).
 template <typename T>
-__device__ __forceinline__ T softened_w(T r, T beta) {
+__host__ __device__ __forceinline__ T softened_w(T r, T beta) {
     const T half_beta = beta * (T)0.5;
     const T r2 = r * r;
     const T r3 = r2 * r;

@@ -149,6 +149,9 @@ int steps_b200_engine_set_symmetric(steps_b200_engine *e, int on);
 int steps_b200_engine_is_symmetric(steps_b200_engine *e);
 int steps_b200_engine_range(steps_b200_engine *e, int *i_lo, int *i_hi);
 int steps_b200_sym_rules(int n, int nranks, int rank, int ib_size, int *i_lo, int *i_hi, int *rules_out, int max_blocks);
+/* Host-only, pure: the number of j-chunks the action-reaction launch aims for, given the j-tiles of the problem, the i-blocks of the
+ * call, the j-side rows one pass holds and the resident-CTA slots of the GPU (see engine.cu; 56 unless a pass would have < 24 waves). */
+int steps_b200_sym_chunk_target(int n_tiles, int n_ib, long long rows_per_pass, int slots);
 /* Test hooks (tests/test_gpu_sym.py): one GPU plays every rank of a P-GPU action-reaction job in turn.
  * debug_set_rank gives the engine the rows and rules of `rank` of `nranks` without a communicator (its evaluation
  * then skips the all-reduce); debug_fsym reads the engine's j-side sums ([3][n_pad] REALs of the engine's precision) and/or replaces them by

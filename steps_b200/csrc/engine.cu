@@ -588,6 +588,23 @@ bool sym_call(const steps_b200_engine *e, int id_min, int n_i) {
     return e->sym && id_min == e->i_lo && n_i == e->i_hi - e->i_lo && n_i > 0;
 }
 
+}  // namespace
+
+// Number of j-chunks the action-reaction launch aims for (host-only, pure).  56 by default (the production shape of round 1).
+// Large N: only a few j-side rows fit the row buffer, a pass then has few CTAs and its last wave runs mostly empty (modelled with
+// list scheduling of the CTA costs, tools/pass_model.py: 0.88 of the ideal at C5, N = 16.7M FP32, 79 rows per pass).  Shorter chunks
+// restore >= 24 waves of CTAs per pass (0.96), capped at 160 chunks (the i-side partial buffer grows with the chunk count).
+// Nothing changes below 4096 tiles or while rows x 56 >= 24 x slots: C2 and every configuration measured in round 1 keep 56.
+extern "C" int steps_b200_sym_chunk_target(int n_tiles, int n_ib, long long rows_per_pass, int slots) {
+    int target = SYM_TARGET_CHUNKS;
+    if (n_tiles < 4096) return target;
+    long long rows = std::max<long long>(1, std::min<long long>(rows_per_pass, (long long)n_ib));
+    const long long want = 24LL * slots;
+    if (rows * target < want) target = (int)std::min<long long>(160, (want + rows - 1) / rows);
+    return target;
+}
+
+namespace {
 Plan sym_plan(const steps_b200_engine *e, int n_i) {
     const SymVariant sv = sym_shape(e);
     Plan p{};
@@ -598,16 +615,10 @@ Plan sym_plan(const steps_b200_engine *e, int n_i) {
     int target = SYM_TARGET_CHUNKS;
     if (const char *s = getenv("STEPS_B200_SYM_CHUNKS")) {
         target = std::max(1, atoi(s));  // tuning knob
-    } else if (p.n_tiles >= 4096) {
-        // Large N: only a few j-side rows fit the row buffer, a pass then has few CTAs and its last wave runs mostly empty
-        // (modelled with list scheduling of the CTA costs: 0.88 of the ideal at C5, N = 16.7M FP32, 79 rows per pass).  Shorter
-        // chunks restore >= 24 waves of CTAs per pass (0.96).  Nothing changes while rows x 56 >= 24 x slots: C2 and every
-        // configuration measured in round 1 keep their 56 chunks.
+    } else {
         const size_t row_bytes = (size_t)3 * e->n_pad * e->real_bytes;
-        size_t rows = e->gpart_bytes ? e->gpart_bytes / row_bytes : std::max<size_t>(1, ((size_t)16 << 30) / row_bytes);
-        rows = std::max<size_t>(1, std::min<size_t>(rows, (size_t)p.n_ib));
-        const size_t want = (size_t)24 * p.slots;
-        if (rows * (size_t)target < want) target = (int)std::min<size_t>(160, (want + rows - 1) / rows);
+        const size_t rows = e->gpart_bytes ? e->gpart_bytes / row_bytes : std::max<size_t>(1, ((size_t)16 << 30) / row_bytes);
+        target = steps_b200_sym_chunk_target(p.n_tiles, p.n_ib, (long long)rows, p.slots);
     }
     p.tiles_per_chunk = std::max(MIN_TILES_PER_CHUNK, (p.n_tiles + target - 1) / target);
     p.n_chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;

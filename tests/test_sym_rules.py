@@ -76,3 +76,27 @@ def test_work_is_balanced(nranks):
 def test_rejects_bad_geometry():
     assert api.sym_rules(700, 1, 0, 768) is None        # fewer than two i-blocks
     assert api.sym_rules(100000, 4, 0, 700) is None     # i-block not a multiple of the j-tile
+
+
+def test_chunk_target_of_the_action_reaction_plan():
+    """steps_b200_sym_chunk_target (host-only): 56 chunks for everything measured in round 1, more and shorter chunks only when a
+    pass of a very large problem would hold fewer than 24 waves of CTAs (tools/pass_model.py)"""
+    from steps_b200 import _lib
+
+    f = _lib.load().steps_b200_sym_chunk_target
+    sms = 148
+    # C2: N = 2M FP64, i-block 768, 2 CTAs/SM, 341 rows of 48 MB in 16 GB
+    assert f(15625, 2605, 341, sms * 2) == 56
+    # C2 on 8 GPUs: 326 own i-blocks per rank
+    assert f(15625, 326, 341, sms * 2) == 56
+    # FP32 at N = 2M (i-block 1024, 4 CTAs/SM): every row fits
+    assert f(15625, 1954, 1954, sms * 4) == 56
+    # small problems never change
+    assert f(3125, 521, 521, sms * 2) == 56 and f(71, 12, 1, sms * 2) == 56
+    # C5: N = 16.7M FP32, 79 rows of 201 MB per pass -> capped at 160 chunks
+    assert f(131072, 16384, 79, sms * 4) == 160
+    # C4 with the S^1xR^2 action-reaction kernel: i-block 384, 160 rows of 100 MB
+    assert f(32768, 10923, 160, sms * 4) == 89
+    # monotone in the rows a pass holds
+    vals = [f(131072, 16384, r, sms * 4) for r in (40, 79, 160, 320, 640)]
+    assert vals == sorted(vals, reverse=True) and vals[-1] == 56

@@ -193,6 +193,14 @@ int steps_b200_engine_init_errmax(steps_b200_engine *e, double a, double hubble,
 int steps_b200_engine_kdk_step(steps_b200_engine *e, double h, double a_old, double hubble_old, double a_new,
                                double hubble_new, double *errmax_out);
 
+/* GLASS_MAKING builds of the reference: G = -1 (global_variables.h:19-23) and the diagnostics step() accumulates in
+ * that mode (step.cc:107-121, :143-148, :270-303).  set_glass_making(e, 1) switches kdk_step / init_errmax of the engine to that
+ * build's arithmetic; after a step glass_stats() returns, in the argument order of Log_write_glass (inputoutput.cc:974),
+ * {F_mean, Fmax, A_mean, A_max, dmean, dmax, V_mean, V_max} over ALL N particles (all-reduced in a multi-GPU job), internal units.
+ * The velocities are zeroed by the caller before the upload, as main.cc:1240-1254 does. */
+int steps_b200_engine_set_glass_making(steps_b200_engine *e, int on);
+int steps_b200_engine_glass_stats(steps_b200_engine *e, double *out8);
+
 /* device timers (CUDA events on the engine's stream): milliseconds of the last force evaluation
  * (pack + pair kernels + reduce) and of the last complete kdk_step. */
 int steps_b200_engine_timings(steps_b200_engine *e, double *force_ms, double *step_ms);
@@ -228,6 +236,8 @@ int steps_b200_group_init_errmax(steps_b200_group *g, double a, double hubble, d
 int steps_b200_group_kdk_step(steps_b200_group *g, double h, double a_old, double hubble_old, double a_new, double hubble_new,
                               double *errmax_out);
 /* gather the state to host arrays [3N]: x from the replica, v and F from each owner; any may be NULL */
+int steps_b200_group_set_glass_making(steps_b200_group *g, int on);
+int steps_b200_group_glass_stats(steps_b200_group *g, double *out8);
 int steps_b200_group_download(steps_b200_group *g, void *x, void *v, void *F);
 
 /* ------------------------------------------------------------------------------------------

@@ -37,7 +37,8 @@ def load() -> C.CDLL:
         _lib.oracle_force_softening_f64.argtypes = [C.c_double, C.c_double]
         _lib.oracle_force_softening_f32.restype = C.c_float
         _lib.oracle_force_softening_f32.argtypes = [C.c_float, C.c_float]
-        for f in ("oracle_kick_errmax_f64", "oracle_kick_errmax_f32", "oracle_friedmann_step", "oracle_hubble"):
+        for f in ("oracle_kick_errmax_f64", "oracle_kick_errmax_f32", "oracle_glass_kick_errmax_f64", "oracle_glass_kick_errmax_f32",
+                  "oracle_friedmann_step", "oracle_hubble"):
             getattr(_lib, f).restype = C.c_double
         _lib.oracle_friedmann_step.argtypes = [C.c_double] * 7
         _lib.oracle_hubble.argtypes = [C.c_double] * 6
@@ -122,6 +123,27 @@ def kick_errmax(g, v, F, a, hubble, h, do_kick=1) -> float:
     return float(getattr(lib, "oracle_kick_errmax" + _sfx(g))(C.byref(p), v.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p),
                                                                g.SOFT_LENGTH.ctypes.data_as(C.c_void_p), C.c_double(a), C.c_double(hubble),
                                                                C.c_double(h), do_kick))
+
+
+def glass_kick_drift(g, x, v, F, a, hubble, h):
+    """GLASS_MAKING first half (step.cc:129-181 with G = -1): returns (sum of displacements, max displacement)"""
+    lib, keep = load(), []
+    p = _params(g, 0, keep)
+    out = (C.c_double * 2)()
+    getattr(lib, "oracle_glass_kick_drift" + _sfx(g))(C.byref(p), x.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p),
+                                                       F.ctypes.data_as(C.c_void_p), C.c_double(a), C.c_double(hubble), C.c_double(h), out)
+    return out[0], out[1]
+
+
+def glass_kick_errmax(g, v, F, a, hubble, h):
+    """GLASS_MAKING second half (step.cc:254-303 with G = -1): returns errmax, (sum|F|, max|F|, sum|A|, max|A|, sum|v|, max|v|)"""
+    lib, keep = load(), []
+    p = _params(g, 0, keep)
+    out = (C.c_double * 6)()
+    e = float(getattr(lib, "oracle_glass_kick_errmax" + _sfx(g))(C.byref(p), v.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p),
+                                                                  g.SOFT_LENGTH.ctypes.data_as(C.c_void_p), C.c_double(a), C.c_double(hubble),
+                                                                  C.c_double(h), out))
+    return e, tuple(out)
 
 
 def friedmann_step(g, a0, h) -> float:

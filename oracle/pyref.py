@@ -141,6 +141,23 @@ class Reference:
         self.lib.sref_kdk_state(x.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p))
         return x, v, F
 
+    @property
+    def is_glass(self) -> bool:
+        return bool(self.lib.sref_is_glass())
+
+    def set_out_dir(self, path: str) -> None:
+        """directory (with trailing separator) the reference writes its log files to (OUT_DIR)"""
+        if not path.endswith(os.sep):
+            path += os.sep
+        self.lib.sref_set_out_dir(path.encode())
+        self._out_dir = path
+
+    def glass_log(self) -> np.ndarray:
+        """rows of <OUT_DIR>Glass_logfile.dat written by the GLASS_MAKING step() (Log_write_glass, inputoutput.cc:974-1060):
+        columns 6..13 = Mean(F) Max(F) Mean(A) Max(A) Mean(disp) Max(disp) Mean(v)[km/s] Max(v)[km/s], printed with %.15f"""
+        rows = [ln.split() for ln in open(os.path.join(self._out_dir, "Glass_logfile.dat")) if ln.strip() and not ln.startswith("#")]
+        return np.array([[float(v) for v in r] for r in rows])
+
     def friedmann_step(self, a0: float, h: float) -> float:
         return float(self.lib.sref_friedmann_step(a0, h))
 

@@ -303,6 +303,21 @@ void sref_kdk_state(REAL *xo, REAL *vo, REAL *Fo)
     if (Fo) memcpy(Fo, F, sizeof(REAL) * 3 * (size_t)N);
 }
 
+/* GLASS_MAKING builds: step() appends its diagnostics to <OUT_DIR>Glass_logfile.dat (Log_write_glass, inputoutput.cc:974) */
+int sref_is_glass(void)
+{
+#ifdef GLASS_MAKING
+    return 1;
+#else
+    return 0;
+#endif
+}
+void sref_set_out_dir(const char *dir)
+{
+    strncpy(OUT_DIR, dir, sizeof(OUT_DIR) - 1);
+    OUT_DIR[sizeof(OUT_DIR) - 1] = 0;
+}
+
 double sref_friedmann_step(double a0, double hh) { return friedmann_solver_step(a0, hh); }
 double sref_hubble(double aa) { return CALCULATE_Hubble_param(aa); }
 

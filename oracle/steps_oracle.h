@@ -35,6 +35,11 @@ void oracle_kick_drift_f64(const oracle_params *p, double *x, double *v, const d
 void oracle_kick_drift_f32(const oracle_params *p, float *x, float *v, const float *F, double a, double hubble, double h);
 double oracle_kick_errmax_f64(const oracle_params *p, double *v, const double *F, const double *soft, double a, double hubble, double h, int do_kick);
 double oracle_kick_errmax_f32(const oracle_params *p, float *v, const float *F, const float *soft, double a, double hubble, double h, int do_kick);
+/* GLASS_MAKING build of step() (G = -1, step.cc:107-148, :254-303): see steps_oracle_impl.h */
+void oracle_glass_kick_drift_f64(const oracle_params *p, double *x, double *v, const double *F, double a, double hubble, double h, double *out2);
+void oracle_glass_kick_drift_f32(const oracle_params *p, float *x, float *v, const float *F, double a, double hubble, double h, double *out2);
+double oracle_glass_kick_errmax_f64(const oracle_params *p, double *v, const double *F, const double *soft, double a, double hubble, double h, double *out6);
+double oracle_glass_kick_errmax_f32(const oracle_params *p, float *v, const float *F, const float *soft, double a, double hubble, double h, double *out6);
 double oracle_friedmann_step(double H0, double Om, double Or, double Ol, double Ok, double a0, double h);
 double oracle_hubble(double H0, double Om, double Or, double Ol, double Ok, double a);
 

@@ -271,6 +271,65 @@ double FN(oracle_kick_errmax)(const oracle_params *p, REAL *v, const REAL *F, co
     return (double)errmax;
 }
 
+/* ---- GLASS_MAKING build of step(): G = -1.0 (global_variables.h:19-23) and the diagnostics ---- */
+
+/* step.cc:129-148: first half kick + drift (+ wrap :151-180) with the displacement statistics; out2 = {sum of disp, max disp} */
+void FN(oracle_glass_kick_drift)(const oracle_params *p, REAL *x, REAL *v, const REAL *F, double a, double hubble, double h, double *out2)
+{
+    const REAL a3 = (REAL)pow(a, -3.0), L = (REAL)p->L;
+    REAL dmean = 0, dmax = 0;
+    for (int i = 0; i < p->n; i++) {
+        for (int k = 0; k < 3; k++) {
+            REAL acc = (REAL)(-1.0 * F[3 * i + k] * a3 - 2.0 * (REAL)hubble * v[3 * i + k]);
+            v[3 * i + k] += acc * (REAL)(h / 2.0);
+            x[3 * i + k] = x[3 * i + k] + v[3 * i + k] * (REAL)h;
+        }
+        REAL d0 = v[3 * i] * (REAL)h, d1 = v[3 * i + 1] * (REAL)h, d2 = v[3 * i + 2] * (REAL)h;
+        REAL disp = (REAL)sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        dmean += disp;
+        if (dmax <= disp) dmax = disp;
+    }
+    for (int i = 0; i < p->n; i++)
+        for (int k = 0; k < 3; k++)
+            if (p->topology == 1 || ((p->topology == 2 || p->topology == 3) && k == 2)) {
+                REAL xx = x[3 * i + k];
+                if (xx < 0) xx = xx + L;
+                else if (xx >= L) xx = xx - L;
+                x[3 * i + k] = xx;
+            }
+    out2[0] = (double)dmean;
+    out2[1] = (double)dmax;
+}
+
+/* step.cc:254-303: second half kick + errmax + force / acceleration / velocity statistics;
+ * out6 = {sum |F|, max |F|, sum |A|, max |A|, sum |v|, max |v|} */
+double FN(oracle_glass_kick_errmax)(const oracle_params *p, REAL *v, const REAL *F, const REAL *soft, double a, double hubble, double h,
+                                    double *out6)
+{
+    const REAL a3 = (REAL)pow(a, -3.0);
+    REAL errmax = 0, Fm = 0, Fx = 0, Am = 0, Ax = 0, Vm = 0, Vx = 0;
+    for (int i = 0; i < p->n; i++) {
+        REAL acc[3];
+        for (int k = 0; k < 3; k++) {
+            acc[k] = (REAL)(-1.0 * F[3 * i + k] * a3 - 2.0 * (REAL)hubble * v[3 * i + k]);
+            v[3 * i + k] += acc[k] * (REAL)(h / 2.0);
+        }
+        REAL A_abs = (REAL)sqrt(acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2]);
+        REAL err = A_abs / soft[i];
+        if (err > errmax) errmax = err;
+        REAL F_abs = (REAL)sqrt(F[3 * i] * F[3 * i] + F[3 * i + 1] * F[3 * i + 1] + F[3 * i + 2] * F[3 * i + 2]);
+        Fm += F_abs;
+        if (F_abs > Fx) Fx = F_abs;
+        Am += A_abs;
+        if (A_abs > Ax) Ax = A_abs;
+        REAL V_abs = (REAL)sqrt(v[3 * i] * v[3 * i] + v[3 * i + 1] * v[3 * i + 1] + v[3 * i + 2] * v[3 * i + 2]);
+        Vm += V_abs;
+        if (V_abs > Vx) Vx = V_abs;
+    }
+    out6[0] = (double)Fm; out6[1] = (double)Fx; out6[2] = (double)Am; out6[3] = (double)Ax; out6[4] = (double)Vm; out6[5] = (double)Vx;
+    return (double)errmax;
+}
+
 #undef FN
 #undef CAT
 #undef CAT_

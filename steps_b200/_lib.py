@@ -101,6 +101,10 @@ SYMBOLS = {
     "steps_b200_engine_download": (_I, [_VP, _VP, _VP, _VP]),
     "steps_b200_engine_init_errmax": (_I, [_VP, _D, _D, _PD]),
     "steps_b200_engine_kdk_step": (_I, [_VP, _D, _D, _D, _D, _D, _PD]),
+    "steps_b200_engine_set_glass_making": (_I, [_VP, _I]),
+    "steps_b200_engine_glass_stats": (_I, [_VP, _PD]),
+    "steps_b200_group_set_glass_making": (_I, [_VP, _I]),
+    "steps_b200_group_glass_stats": (_I, [_VP, _PD]),
     "steps_b200_engine_timings": (_I, [_VP, _PD, _PD]),
     "steps_b200_engine_pair_kernel_ms": (_I, [_VP, _PD]),
     "steps_b200_engine_mark": (_I, [_VP, _I]),

@@ -389,6 +389,17 @@ class Engine:
         self.a, self.Hubble_param, self.errmax = a_new, H_new, e.value
         return self.errmax
 
+    def set_glass_making(self, on: bool) -> None:
+        """the arithmetic of a -DGLASS_MAKING build: G = -1 (global_variables.h:19-23) and the diagnostics of step.cc:143-148, :270-303.
+        The caller zeroes the velocities before upload(), as main.cc:1240-1254 does."""
+        check(self.lib.steps_b200_engine_set_glass_making(self._h, 1 if on else 0))
+
+    def glass_stats(self) -> dict:
+        """diagnostics of the last step() in glass-making mode, named as the arguments of Log_write_glass (inputoutput.cc:974)"""
+        out = (C.c_double * 8)()
+        check(self.lib.steps_b200_engine_glass_stats(self._h, out))
+        return dict(zip(("F_mean", "Fmax", "A_mean", "A_max", "dmean", "dmax", "V_mean", "V_max"), out))
+
     def next_h(self) -> float:
         """main.cc:1834-1842"""
         return self.lib.steps_b200_next_timestep(self.g.ACC_PARAM, self.errmax, self.g.h_min, self.g.h_max)

@@ -18,6 +18,7 @@
 
 #include "../../include/steps_b200.h"
 #include "aux_kernels.cuh"
+#include "glass_kernels.cuh"
 #include "ewald_t3.cuh"
 #include "ewald_s1r2.cuh"
 #include "radial_table.cuh"
@@ -231,6 +232,12 @@ struct steps_b200_engine {
     void *d_gpart = nullptr, *d_fsym = nullptr;  // REAL of the build
     size_t gpart_bytes = 0;
     Plan last_sym_plan{};        // plan of the last action-reaction evaluation (the debug hook redoes its final reduction)
+    // GLASS_MAKING mode: G = -1 and the diagnostics of step.cc:143-148, :270-303
+    bool glass = false;
+    double *d_glass_part = nullptr;  // [blocks][2*GLASS_NQ] per-block (sum, max) pairs
+    double *d_glass = nullptr;       // [2*GLASS_NQ] reduced over this engine's rows
+    int glass_blocks = 0;
+    double h_glass[2 * GLASS_NQ] = {};  // after the last step: (sum, max) of displacement, force, acceleration, velocity over ALL rows
 };
 
 namespace {
@@ -991,7 +998,7 @@ KdkScalars kdk_scalars(const steps_b200_engine *e, double h, double a, double hu
         k.h = h;
     }
     k.L = e->p.L;
-    k.G = 1.0;
+    k.G = e->glass ? -1.0 : 1.0;  // global_variables.h:19-23
     k.topology = e->p.topology;
     return k;
 }
@@ -1095,7 +1102,7 @@ extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym};
+    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym, e->d_glass_part, e->d_glass};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (e->h_errmax) cudaFreeHost(e->h_errmax);
@@ -1286,6 +1293,65 @@ extern "C" int steps_b200_engine_init_errmax(steps_b200_engine *e, double a, dou
     return reduce_errmax(e, errmax_out);
 }
 
+// One KDK step of a GLASS_MAKING build (step.cc with G = -1 and the diagnostics of :143-148, :270-303); same sequence as the
+// ordinary step below with the glass kernels, one small reduction launch per half and, multi-GPU, two tiny all-reduces.
+template <typename T>
+static int glass_kdk_step(steps_b200_engine *e, double h, double a_old, double hubble_old, double a_new, double hubble_new, double *errmax_out) {
+    const int cnt = e->i_hi - e->i_lo;
+    const int blocks = std::max(1, (cnt + 255) / 256);
+    if (blocks > e->glass_blocks) {
+        if (e->d_glass_part) CU_TRY(cudaFree(e->d_glass_part));
+        e->d_glass_part = nullptr;
+        e->glass_blocks = 0;
+        CU_TRY(cudaMalloc(&e->d_glass_part, (size_t)blocks * 2 * GLASS_NQ * sizeof(double)));
+        e->glass_blocks = blocks;
+    }
+    if (!e->d_glass) CU_TRY(cudaMalloc(&e->d_glass, 2 * GLASS_NQ * sizeof(double)));
+    CU_TRY(cudaMemsetAsync(e->d_glass_part, 0, (size_t)blocks * 2 * GLASS_NQ * sizeof(double), e->stream));
+    const KdkScalars k0 = kdk_scalars(e, h, a_old, hubble_old);
+    glass_kick_drift_kernel<T><<<blocks, 256, 0, e->stream>>>((T *)e->d_x, (T *)e->d_v, (const T *)e->d_F, e->i_lo, e->i_hi, k0, e->d_glass_part);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    glass_finish_kernel<<<1, 256, 0, e->stream>>>(e->d_glass_part, blocks, 0, 1, e->d_glass);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    if (gather_positions(e)) return 1;
+    if (forces_impl(e, e->i_lo, e->i_hi - 1)) return 1;
+    const KdkScalars k1 = kdk_scalars(e, h, a_new, hubble_new);
+    CU_TRY(cudaMemsetAsync(e->d_errmax, 0, sizeof(double), e->stream));
+    glass_kick_errmax_kernel<T><<<blocks, 256, 0, e->stream>>>((T *)e->d_v, (const T *)e->d_F, (const T *)e->d_s, e->i_lo, e->i_hi, k1, e->d_errmax,
+                                                               e->d_glass_part);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    glass_finish_kernel<<<1, 256, 0, e->stream>>>(e->d_glass_part, blocks, 1, GLASS_NQ, e->d_glass);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    if (e->nranks > 1 && e->comm) {
+        NCCL_TRY(g_nccl.AllReduce(e->d_glass, e->d_glass, GLASS_NQ, ncclFloat64, ncclSum, e->comm, e->stream));
+        NCCL_TRY(g_nccl.AllReduce(e->d_glass + GLASS_NQ, e->d_glass + GLASS_NQ, GLASS_NQ, ncclFloat64, ncclMax, e->comm, e->stream));
+    }
+    CU_TRY(cudaMemcpyAsync(e->h_glass, e->d_glass, 2 * GLASS_NQ * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    return reduce_errmax(e, errmax_out);  // synchronises the stream: h_glass is valid afterwards
+}
+
+extern "C" int steps_b200_engine_set_glass_making(steps_b200_engine *e, int on) {
+    if (!e) return fail("engine is NULL");
+    e->glass = on != 0;
+    return 0;
+}
+
+extern "C" int steps_b200_engine_glass_stats(steps_b200_engine *e, double *out8) {
+    if (!e || !out8) return fail("engine or output is NULL");
+    if (!e->glass) return fail("engine is not in glass-making mode");
+    const double n = (double)e->n;
+    // argument order of Log_write_glass (inputoutput.cc:974): F_mean, Fmax, A_mean, A_max, dmean, dmax, V_mean, V_max
+    out8[0] = e->h_glass[1] / n; out8[1] = e->h_glass[GLASS_NQ + 1];
+    out8[2] = e->h_glass[2] / n; out8[3] = e->h_glass[GLASS_NQ + 2];
+    out8[4] = e->h_glass[0] / n; out8[5] = e->h_glass[GLASS_NQ + 0];
+    out8[6] = e->h_glass[3] / n; out8[7] = e->h_glass[GLASS_NQ + 3];
+    return 0;
+}
+
 extern "C" int steps_b200_engine_kdk_step(steps_b200_engine *e, double h, double a_old, double hubble_old, double a_new,
                                           double hubble_new, double *errmax_out) {
     if (!e) return fail("engine is NULL");
@@ -1293,6 +1359,9 @@ extern "C" int steps_b200_engine_kdk_step(steps_b200_engine *e, double h, double
     DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
     CU_TRY(cudaEventRecord(e->ev[2], e->stream));
+    if (e->glass)
+        return e->real_bytes == 8 ? glass_kdk_step<double>(e, h, a_old, hubble_old, a_new, hubble_new, errmax_out)
+                                  : glass_kdk_step<float>(e, h, a_old, hubble_old, a_new, hubble_new, errmax_out);
     const int cnt = e->i_hi - e->i_lo;
     const KdkScalars k0 = kdk_scalars(e, h, a_old, hubble_old);
     if (e->real_bytes == 8)
@@ -1736,6 +1805,19 @@ extern "C" int steps_b200_group_kdk_step(steps_b200_group *g, double h, double a
 }
 
 // x: full (every engine holds the gathered replica -- taken from engine 0); v, F: each engine's owned rows
+extern "C" int steps_b200_group_set_glass_making(steps_b200_group *g, int on) {
+    if (!g) return fail("group is NULL");
+    for (auto *e : g->eng)
+        if (steps_b200_engine_set_glass_making(e, on)) return 1;
+    return 0;
+}
+
+// every engine of the group holds the all-reduced diagnostics after a step: engine 0's copy is returned
+extern "C" int steps_b200_group_glass_stats(steps_b200_group *g, double *out8) {
+    if (!g || g->eng.empty()) return fail("group is NULL");
+    return steps_b200_engine_glass_stats(g->eng[0], out8);
+}
+
 extern "C" int steps_b200_group_download(steps_b200_group *g, void *x, void *v, void *F) {
     if (!g) return fail("group is NULL");
     const size_t rb = g->real_bytes;

@@ -11,7 +11,9 @@
 // set STEPS_B200_LAZY_HOST_STATE=1 to refresh them only every call of steps_b200_shim_sync_host()).
 //
 // Scope: one MPI rank (numtasks == 1) driving n_GPU devices, the reference's `StePS_CUDA <param> <nGPU>`
-// mode.  GLASS_MAKING diagnostics (step.cc:143-148, :270-303) are not produced.
+// mode.  A -DGLASS_MAKING build switches the engines to that build's arithmetic (G = -1) and reproduces its diagnostics
+// (step.cc:143-148, :270-303): the eight statistics are reduced on the device, printed and passed to Log_write_glass as the
+// reference does (the device kernels of this mode have not run on a GPU yet, see glass_kernels.cuh).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +23,9 @@
 #include "steps_b200.h"
 
 void recalculate_softening();
+#ifdef GLASS_MAKING
+void Log_write_glass(REAL F_mean, REAL Fmax, REAL A_mean, REAL A_max, REAL dmean, REAL dmax, REAL V_mean, REAL V_max);  // inputoutput.cc:974 (declared in step.cc:32)
+#endif
 
 namespace {
 steps_b200_group *g_group = nullptr;
@@ -83,6 +88,9 @@ bool ensure_resident(REAL *xx, REAL *vv, REAL *FF) {
     const char *lazy = getenv("STEPS_B200_LAZY_HOST_STATE");
     g_lazy = lazy && atoi(lazy) != 0;
     if (steps_b200_group_create(&g_group, &p, (int)sizeof(REAL), n_GPU > 0 ? n_GPU : 1, dev ? atoi(dev) : 0)) return fail("engine creation");
+#ifdef GLASS_MAKING
+    if (steps_b200_group_set_glass_making(g_group, 1)) return fail("glass-making mode");
+#endif
     if (steps_b200_group_upload(g_group, xx, vv, M, SOFT_LENGTH, FF)) return fail("state upload");
     return true;
 }
@@ -152,5 +160,22 @@ void step(REAL *xx, REAL *vv, REAL *FF) {
     errmax = (REAL)e;
     if (!g_lazy && steps_b200_group_download(g_group, xx, vv, FF)) fail("state download");
     printf("KDK Leapfrog integration...done.\n");
+#ifdef GLASS_MAKING
+    {
+        // step.cc:287-302: the statistics of this step, reduced on the device (means over all N particles)
+        double gs[8];
+        if (steps_b200_group_glass_stats(g_group, gs)) {
+            fail("glass-making statistics");
+            return;
+        }
+        const REAL F_mean = (REAL)gs[0], Fmax = (REAL)gs[1], A_mean = (REAL)gs[2], A_max = (REAL)gs[3], dmean = (REAL)gs[4], dmax = (REAL)gs[5],
+                   V_mean = (REAL)gs[6], V_max = (REAL)gs[7];
+        if (dmax > 1.0)
+            printf("Glass making:\tF_max=%e\tA_max = %e\n\t\tdisp-mean=%fMpc\tdisp-maximum = %fMpc\n\t\tV_mean = %e\tV_max = %e\n", Fmax, A_max, dmean, dmax, V_mean, V_max);
+        else
+            printf("Glass making:\tF_max=%e\tA_max = %e\n\t\tdisp-mean=%fkpc\tdisp-maximum = %fkpc\n\t\tV_mean = %e\tV_max = %e\n", Fmax, A_max, dmean * 1000, dmax * 1000, V_mean, V_max);
+        Log_write_glass(F_mean, Fmax, A_mean, A_max, dmean, dmax, V_mean, V_max);
+    }
+#endif
     printf("Timestep wall-clock time = %fs\n", omp_get_wtime() - t0);
 }

@@ -2,6 +2,7 @@
 # First GPU call of the next round: verify and measure what round 1 had to leave unverified (its GPU budget ran out):
 #   1. the S^1xR^2 action-reaction kernel (pair_s1r2_sym.cuh, opt-in): tests, then every shape against the one-sided kernel
 #   1b. the action-reaction kernel of the table-lookup topologies (pair_generic_sym.cuh, opt-in, never run): tests + sweep
+#   1c. glass-making mode of the KDK step (never run): tests
 #   2. ncu --set full of the FP32 action-reaction kernel (the round-1 capture was cut off mid-replay)
 #   3. full regression + bench on the same box
 TAG=${1:-r2a}
@@ -31,6 +32,9 @@ for v in 0 1 2 3 4 5; do
   STEPS_B200_GEN_SYM=1 STEPS_B200_GEN_SYM_VARIANT=$v timeout 200 python tools/topo_bench.py t3:64,s1r2:200000 >> $O/${TAG}_generic_sweep.txt 2>&1
 done
 cut -c1-300 $O/${TAG}_generic_sweep.txt
+stamp "glass-making mode (glass_kernels.cuh, never run): engine vs the CPU port, drop-in glass build vs the reference's"
+STEPS_B200_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_glass.py -m gpu -q -s --timeout 120 > $O/${TAG}_glass_tests.log 2>&1
+echo "rc=$?" >> $O/${TAG}_glass_tests.log; grep -E "^glass|passed|failed|rc=|Error|assert" $O/${TAG}_glass_tests.log | cut -c1-260 | tail -12
 stamp "ncu --set full, one launch of the FP32 action-reaction kernel at N=400k"
 timeout 240 ncu --set full --clock-control none --import-source on -k regex:force_r3_f32_sym -s 1 -c 1 -o $O/${TAG}_sym_f32_n400k \
     python tools/ncu_f32_sym.py 400000 > $O/${TAG}_ncu_full_f32.out 2>&1

@@ -7,6 +7,7 @@
 // usage: pair_host_check t3 <table.bin> <ngrid> <L> <is_periodic> <n_pairs> <seed> <soft>
 //        pair_host_check s1r2 <table.bin> <nrho> <nz> <rho_max> <L> <order> <n_pairs> <seed> <soft>
 // prints: max relative differences (1) (2) (3), scale = |t| of the pair
+//        pair_host_check forces_t3 | forces_s1r2 ...: a whole force evaluation formed pair-symmetrically (see forces_sym)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -73,9 +74,68 @@ static int run(TopoParams tp, int n_pairs, unsigned seed, double soft, double bo
     return 0;
 }
 
+// whole force evaluation the way the action-reaction kernel forms it: every unordered pair once (t applied to both particles with
+// opposite signs), the self pair one-sidedly; LEAN = the lean T^3 arithmetic.  state.bin = x[3n] M[n] soft[n] (doubles).
+template <int TOPO>
+static int forces_sym(TopoParams tp, const char *state_path, int n, bool lean, const char *out_path) {
+    const std::vector<double> st = load(state_path);
+    if ((int)st.size() != 5 * n) return 6;
+    const double *x = st.data(), *M = x + 3 * n, *S = M + n;
+    T3Fast fk;
+    fk.L = tp.L;
+    fk.halfL = 0.5 * tp.L;
+    fk.inv_h = tp.dim0 > 0 ? (double)tp.dim0 / tp.L : 0.0;
+    fk.N = tp.dim0;
+    std::vector<double> F(3 * (size_t)n, 0.0);
+    for (int i = 0; i < n; ++i) {
+        pair_exact<double, TOPO>(tp, x[3 * i], x[3 * i + 1], x[3 * i + 2], S[i], x[3 * i], x[3 * i + 1], x[3 * i + 2], M[i], S[i], F[3 * i], F[3 * i + 1],
+                                 F[3 * i + 2]);
+        for (int j = i + 1; j < n; ++j) {
+            double t[3];
+            if (TOPO == 1 && lean)
+                pair_t3_fast_unit<double>(fk, static_cast<const double *>(tp.table), x[3 * i], x[3 * i + 1], x[3 * i + 2], S[i], x[3 * j], x[3 * j + 1],
+                                          x[3 * j + 2], S[j], t[0], t[1], t[2]);
+            else
+                pair_exact_unit<double, TOPO>(tp, x[3 * i], x[3 * i + 1], x[3 * i + 2], S[i], x[3 * j], x[3 * j + 1], x[3 * j + 2], S[j], t[0], t[1], t[2]);
+            for (int k = 0; k < 3; ++k) {
+                F[3 * i + k] += M[j] * t[k];
+                F[3 * j + k] -= M[i] * t[k];
+            }
+        }
+    }
+    FILE *f = fopen(out_path, "wb");
+    if (!f) return 7;
+    fwrite(F.data(), sizeof(double), F.size(), f);
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
     TopoParams tp{};
+    // pair_host_check forces_t3 <table.bin> <ngrid> <L> <is_periodic> <state.bin> <n> <lean 0|1> <out.bin>
+    if (!strcmp(argv[1], "forces_t3") && argc == 10) {
+        const std::vector<double> tab = load(argv[2]);
+        tp.topology = 1;
+        tp.dim0 = tp.dim1 = atoi(argv[3]);
+        tp.L = atof(argv[4]);
+        tp.is_periodic = atoi(argv[5]);
+        tp.table = tab.data();
+        return forces_sym<1>(tp, argv[6], atoi(argv[7]), atoi(argv[8]) != 0, argv[9]);
+    }
+    // pair_host_check forces_s1r2 <table.bin> <nrho> <nz> <rho_max> <L> <order> <state.bin> <n> <out.bin>
+    if (!strcmp(argv[1], "forces_s1r2") && argc == 11) {
+        const std::vector<double> tab = load(argv[2]);
+        tp.topology = 2;
+        tp.dim0 = atoi(argv[3]);
+        tp.dim1 = atoi(argv[4]);
+        tp.rho_max = atof(argv[5]);
+        tp.L = atof(argv[6]);
+        tp.order = atoi(argv[7]);
+        tp.is_periodic = 2;
+        tp.table = tab.data();
+        return forces_sym<2>(tp, argv[8], atoi(argv[9]), false, argv[10]);
+    }
     if (!strcmp(argv[1], "t3") && argc == 9) {
         const std::vector<double> tab = load(argv[2]);
         tp.topology = 1;

@@ -32,6 +32,12 @@ for v in 0 1 2 3 4 5; do
   STEPS_B200_GEN_SYM=1 STEPS_B200_GEN_SYM_VARIANT=$v timeout 200 python tools/topo_bench.py t3:64,s1r2:200000 >> $O/${TAG}_generic_sweep.txt 2>&1
 done
 cut -c1-300 $O/${TAG}_generic_sweep.txt
+stamp "ncu --set full of the T^3 kernels at 48^3: one-sided (L1 wavefronts per load: the bound of DESIGN 3.4) and action-reaction (broadcast hypothesis)"
+timeout 240 ncu --set full --clock-control none --import-source on -k regex:force_generic_kernel -s 1 -c 1 -o $O/${TAG}_t3_onesided_48 \
+    python tools/topo_bench.py t3:48 > $O/${TAG}_ncu_t3_onesided.out 2>&1
+STEPS_B200_GEN_SYM=1 STEPS_B200_GEN_SYM_VARIANT=3 timeout 240 ncu --set full --clock-control none --import-source on -k regex:force_generic_sym -s 1 -c 1 -o $O/${TAG}_t3_sym_48 \
+    python tools/topo_bench.py t3:48 > $O/${TAG}_ncu_t3_sym.out 2>&1
+tail -1 $O/${TAG}_ncu_t3_onesided.out | cut -c1-200; tail -1 $O/${TAG}_ncu_t3_sym.out | cut -c1-200
 stamp "glass-making mode (glass_kernels.cuh, never run): engine vs the CPU port, drop-in glass build vs the reference's"
 STEPS_B200_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_glass.py -m gpu -q -s --timeout 120 > $O/${TAG}_glass_tests.log 2>&1
 echo "rc=$?" >> $O/${TAG}_glass_tests.log; grep -E "^glass|passed|failed|rc=|Error|assert" $O/${TAG}_glass_tests.log | cut -c1-260 | tail -12

@@ -25,17 +25,23 @@ class SrefConfig(C.Structure):
                 ("a_start", C.c_double)]
 
 
-def available(variant: str, shim: bool = False) -> bool:
-    return os.path.exists(os.path.join(REF_DIR, f"libsteps_{'shim' if shim else 'ref'}_{variant}.so"))
+def _kind(shim: bool, cuda: bool) -> str:
+    return "shim" if shim else ("refcuda" if cuda else "ref")
+
+
+def available(variant: str, shim: bool = False, cuda: bool = False) -> bool:
+    return os.path.exists(os.path.join(REF_DIR, f"libsteps_{_kind(shim, cuda)}_{variant}.so"))
 
 
 class Reference:
     """One loaded variant of the reference.  Not re-entrant (the reference is a bag of globals)."""
 
-    def __init__(self, variant: str, shim: bool = False):
+    def __init__(self, variant: str, shim: bool = False, cuda: bool = False):
         """shim=True loads the DROP-IN build instead: the same reference TUs minus forces.cc/step.cc plus
-        steps_b200/csrc/shim/*.cc linked against libstepsb200.so (needs a GPU to compute anything)."""
-        path = os.path.join(REF_DIR, f"libsteps_{'shim' if shim else 'ref'}_{variant}.so")
+        steps_b200/csrc/shim/*.cc linked against libstepsb200.so (needs a GPU to compute anything).
+        cuda=True loads the reference's OWN CUDA build (-DUSE_CUDA, forces_cuda.cu compiled unmodified for sm_100a; `make -C oracle
+        refcuda`): the kernel to beat and a second oracle; needs a GPU and set_n_gpu(>= 1) before forces()."""
+        path = os.path.join(REF_DIR, f"libsteps_{_kind(shim, cuda)}_{variant}.so")
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path}: build with `make -C oracle ref` (needs /root/reference)")
         self.lib = C.CDLL(path)
@@ -46,7 +52,7 @@ class Reference:
         self.topology = self.lib.sref_topology()
         self.shim = bool(self.lib.sref_is_shim())
         assert self.shim == shim
-        if not shim:
+        if not shim and not cuda:
             self.lib.sref_force_softening.restype = self.creal
             self.lib.sref_force_softening.argtypes = [self.creal, self.creal]
         self.lib.sref_table.restype = C.c_void_p

@@ -159,7 +159,7 @@ void sref_get_scalars(double *out4)
     out4[3] = (double)((REAL)H0 * H0 * Omega_lambda);
 }
 
-#ifndef STEPS_SHIM_BUILD
+#if !defined(STEPS_SHIM_BUILD) && !defined(USE_CUDA)
 REAL sref_force_softening(REAL r, REAL b) { return force_softening(r, b); }
 #endif
 /* 1 when forces()/step() of this library are the steps_b200 shims (drop-in build), 0 for the pure reference */

@@ -3,6 +3,7 @@
 #   1. the S^1xR^2 action-reaction kernel (pair_s1r2_sym.cuh, opt-in): tests, then every shape against the one-sided kernel
 #   1b. the action-reaction kernel of the table-lookup topologies (pair_generic_sym.cuh, opt-in, never run): tests + sweep
 #   1c. glass-making mode of the KDK step (never run): tests
+#   1d. the reference's own CUDA kernels on the same GPU (second oracle + the kernel to beat)
 #   2. ncu --set full of the FP32 action-reaction kernel (the round-1 capture was cut off mid-replay)
 #   3. full regression + bench on the same box
 TAG=${1:-r2a}
@@ -38,6 +39,9 @@ timeout 240 ncu --set full --clock-control none --import-source on -k regex:forc
 STEPS_B200_GEN_SYM=1 STEPS_B200_GEN_SYM_VARIANT=3 timeout 240 ncu --set full --clock-control none --import-source on -k regex:force_generic_sym -s 1 -c 1 -o $O/${TAG}_t3_sym_48 \
     python tools/topo_bench.py t3:48 > $O/${TAG}_ncu_t3_sym.out 2>&1
 tail -1 $O/${TAG}_ncu_t3_onesided.out | cut -c1-200; tail -1 $O/${TAG}_ncu_t3_sym.out | cut -c1-200
+stamp "the reference's own CUDA path (forces_cuda.cu for sm_100a): second oracle, then timed against ours on the same rows"
+STEPS_B200_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_reference_cuda.py -m gpu -q -s --timeout 150 2>&1 | grep -E "ours vs|passed|failed|Error" | cut -c1-200 | tee $O/${TAG}_reference_cuda_tests.log
+for cs in "c2 65536" "t3:64 32768" "s1r2nl:400000 32768"; do timeout 300 python tools/bench_ref_cuda.py $cs 2>&1 | tail -1 | cut -c1-600; done | tee $O/${TAG}_reference_cuda_bench.txt
 stamp "glass-making mode (glass_kernels.cuh, never run): engine vs the CPU port, drop-in glass build vs the reference's"
 STEPS_B200_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_glass.py -m gpu -q -s --timeout 120 > $O/${TAG}_glass_tests.log 2>&1
 echo "rc=$?" >> $O/${TAG}_glass_tests.log; grep -E "^glass|passed|failed|rc=|Error|assert" $O/${TAG}_glass_tests.log | cut -c1-260 | tail -12

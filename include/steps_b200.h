@@ -238,6 +238,16 @@ int steps_b200_group_kdk_step(steps_b200_group *g, double h, double a_old, doubl
 /* gather the state to host arrays [3N]: x from the replica, v and F from each owner; any may be NULL */
 int steps_b200_group_set_glass_making(steps_b200_group *g, int on);
 int steps_b200_group_glass_stats(steps_b200_group *g, double *out8);
+/* ASCII snapshots in the reference's format (write_ascii_snapshot, inputoutput.cc:826-909; SURVEY.md 8f.2 -- the HDF5 formats need
+ * libhdf5): per particle "x y z vx vy vz M", each "%.16f\t", x and M times H0_dimless (in REAL precision), v times sqrt(a)*UNIT_V (in
+ * double), zero velocities in a GLASS_MAKING build.  snapshot_ascii_host formats host arrays with a pool of workers (nthreads <= 0: all
+ * cores, at most 16).  group_snapshot_ascii_async copies the resident state out asynchronously (in stream order, pinned staging) and returns;
+ * a background thread formats and writes while the caller goes on stepping; group_snapshot_wait joins it and reports its status (the next
+ * snapshot call and group_destroy wait too). */
+int steps_b200_snapshot_ascii_host(const char *path, const void *x, const void *v, const void *M, int n, int real_bytes,
+                                   double h0_dimless, double a, int zero_velocities, int nthreads);
+int steps_b200_group_snapshot_ascii_async(steps_b200_group *g, const char *path, double h0_dimless, double a, int zero_velocities);
+int steps_b200_group_snapshot_wait(steps_b200_group *g);
 int steps_b200_group_download(steps_b200_group *g, void *x, void *v, void *F);
 
 /* ------------------------------------------------------------------------------------------

@@ -147,6 +147,17 @@ class Reference:
         self.lib.sref_kdk_state(x.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p))
         return x, v, F
 
+    def write_ascii_snapshot(self, out_dir: str, x, v, a: float, t_next: float, h0_independent_units: int = 0) -> str:
+        """the reference's own write_ascii_snapshot (inputoutput.cc:826-909); returns the path of the file it wrote"""
+        if not out_dir.endswith(os.sep):
+            out_dir += os.sep
+        x = np.ascontiguousarray(x, dtype=self.REAL)
+        v = np.ascontiguousarray(v, dtype=self.REAL)
+        self.lib.sref_write_ascii_snapshot.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int]
+        self.lib.sref_write_ascii_snapshot(out_dir.encode(), x.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), a, t_next, h0_independent_units)
+        unit_t = 47.14829951063323  # global_variables.h:16
+        return os.path.join(out_dir, "t%d.dat" % int(round(100 * t_next * unit_t)))
+
     @property
     def is_glass(self) -> bool:
         return bool(self.lib.sref_is_glass())

@@ -51,6 +51,8 @@ void forces(REAL *x, REAL *F, int ID_min, int ID_max);                /* forces.
 /* globals that main.cc defines but global_variables.h does not declare */
 extern double a_prev;
 
+void write_ascii_snapshot(REAL *x, REAL *v);  /* inputoutput.cc:826 (C++ linkage, declared in main.cc) */
+
 extern "C" {
 
 struct sref_config {
@@ -301,6 +303,22 @@ void sref_kdk_state(REAL *xo, REAL *vo, REAL *Fo)
     if (xo) memcpy(xo, x, sizeof(REAL) * 3 * (size_t)N);
     if (vo) memcpy(vo, v, sizeof(REAL) * 3 * (size_t)N);
     if (Fo) memcpy(Fo, F, sizeof(REAL) * 3 * (size_t)N);
+}
+
+/* the reference's own ASCII snapshot writer (inputoutput.cc:826-909) on the state given here; the file is <dir>t<round(100 t_next UNIT_T)>.dat
+ * (COSMOLOGY = 1, OUTPUT_TIME_VARIABLE = 0) */
+int sref_write_ascii_snapshot(const char *dir, const REAL *x0, const REAL *v0, double a_now, double t_next_now, int h0_independent_units)
+{
+    strncpy(OUT_DIR, dir, sizeof(OUT_DIR) - 1);
+    OUT_DIR[sizeof(OUT_DIR) - 1] = 0;
+    memcpy(x, x0, sizeof(REAL) * 3 * (size_t)N);
+    memcpy(v, v0, sizeof(REAL) * 3 * (size_t)N);
+    a = a_now;
+    t_next = t_next_now;
+    OUTPUT_TIME_VARIABLE = 0;
+    H0_INDEPENDENT_UNITS = h0_independent_units;
+    write_ascii_snapshot(x, v);
+    return 0;
 }
 
 /* GLASS_MAKING builds: step() appends its diagnostics to <OUT_DIR>Glass_logfile.dat (Log_write_glass, inputoutput.cc:974) */

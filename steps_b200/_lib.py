@@ -104,6 +104,9 @@ SYMBOLS = {
     "steps_b200_engine_set_glass_making": (_I, [_VP, _I]),
     "steps_b200_engine_glass_stats": (_I, [_VP, _PD]),
     "steps_b200_group_set_glass_making": (_I, [_VP, _I]),
+    "steps_b200_snapshot_ascii_host": (_I, [C.c_char_p, _VP, _VP, _VP, _I, _I, _D, _D, _I, _I]),
+    "steps_b200_group_snapshot_ascii_async": (_I, [_VP, C.c_char_p, _D, _D, _I]),
+    "steps_b200_group_snapshot_wait": (_I, [_VP]),
     "steps_b200_group_glass_stats": (_I, [_VP, _PD]),
     "steps_b200_engine_timings": (_I, [_VP, _PD, _PD]),
     "steps_b200_engine_pair_kernel_ms": (_I, [_VP, _PD]),

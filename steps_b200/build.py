@@ -21,7 +21,7 @@ def _stale(target: str, sources: list) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     csrc = os.path.join(HERE, "csrc")
-    srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cu", ".cuh", ".h"))]
     srcs.append(os.path.join(ROOT, "include", "steps_b200.h"))
     out = os.path.join(HERE, "libstepsb200.so")
     if force or _stale(out, srcs):

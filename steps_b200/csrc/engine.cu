@@ -19,6 +19,7 @@
 #include "../../include/steps_b200.h"
 #include "aux_kernels.cuh"
 #include "glass_kernels.cuh"
+#include "snapshot_io.h"
 #include "ewald_t3.cuh"
 #include "ewald_s1r2.cuh"
 #include "radial_table.cuh"
@@ -1689,6 +1690,7 @@ extern "C" void steps_b200_release_cached(void) {
 struct steps_b200_group {
     std::vector<steps_b200_engine *> eng;
     int n = 0, real_bytes = 8;
+    SnapshotJob snap;  // asynchronous ASCII snapshot in flight (snapshot_io.h)
 };
 
 namespace {
@@ -1718,6 +1720,9 @@ int group_parallel(steps_b200_group *g, Fn fn) {
 
 extern "C" void steps_b200_group_destroy(steps_b200_group *g) {
     if (!g) return;
+    if (g->snap.running) g->snap.th.join();  // a snapshot still being written: finish it before its staging buffers go away
+    for (void *p : {g->snap.hx, g->snap.hv, g->snap.hm})
+        if (p) cudaFreeHost(p);
     for (auto *e : g->eng) steps_b200_engine_destroy(e);
     delete g;
 }
@@ -1805,6 +1810,84 @@ extern "C" int steps_b200_group_kdk_step(steps_b200_group *g, double h, double a
 }
 
 // x: full (every engine holds the gathered replica -- taken from engine 0); v, F: each engine's owned rows
+// ------------------------------------------------------------------------------------------------ snapshots (ASCII)
+extern "C" int steps_b200_snapshot_ascii_host(const char *path, const void *x, const void *v, const void *M, int n, int real_bytes,
+                                              double h0_dimless, double a, int zero_velocities, int nthreads) {
+    if (!path || !x || !M || (!v && !zero_velocities) || n <= 0) return fail("bad arguments");
+    if (real_bytes != 8 && real_bytes != 4) return fail("real_bytes must be 8 or 4");
+    const std::string err = real_bytes == 8
+        ? snapshot_write_ascii<double>(path, (const double *)x, (const double *)v, (const double *)M, (size_t)n, h0_dimless, a, zero_velocities, nthreads)
+        : snapshot_write_ascii<float>(path, (const float *)x, (const float *)v, (const float *)M, (size_t)n, h0_dimless, a, zero_velocities, nthreads);
+    return err.empty() ? 0 : fail(err);
+}
+
+extern "C" int steps_b200_group_snapshot_wait(steps_b200_group *g) {
+    if (!g) return fail("group is NULL");
+    SnapshotJob &j = g->snap;
+    if (j.running) {
+        j.th.join();
+        j.running = false;
+    }
+    if (!j.err.empty()) {
+        const std::string err = j.err;
+        j.err.clear();
+        return fail("snapshot: " + err);
+    }
+    return 0;
+}
+
+// The state of this moment leaves the devices by asynchronous copies (in stream order: after the step that produced it, before the
+// next one touches it); the call returns once they are enqueued.  A background thread waits for the copies, formats and writes.
+extern "C" int steps_b200_group_snapshot_ascii_async(steps_b200_group *g, const char *path, double h0_dimless, double a, int zero_velocities) {
+    if (!g || g->eng.empty() || !path) return fail("bad arguments");
+    if (steps_b200_group_snapshot_wait(g)) return 1;  // one job in flight: its staging buffers are reused
+    SnapshotJob &j = g->snap;
+    const size_t rb = (size_t)g->real_bytes, n = (size_t)g->n;
+    steps_b200_engine *e0 = g->eng[0];
+    {
+        DeviceGuard dg_;
+        CU_TRY(cudaSetDevice(e0->device));
+        if (j.n != n || j.real_bytes != rb) {
+            for (void **p : {&j.hx, &j.hv, &j.hm})
+                if (*p) { cudaFreeHost(*p); *p = nullptr; }
+            CU_TRY(cudaHostAlloc(&j.hx, 3 * n * rb, cudaHostAllocPortable));
+            CU_TRY(cudaHostAlloc(&j.hv, 3 * n * rb, cudaHostAllocPortable));
+            CU_TRY(cudaHostAlloc(&j.hm, n * rb, cudaHostAllocPortable));
+            j.n = n;
+            j.real_bytes = rb;
+        }
+    }
+    std::vector<cudaEvent_t> done(g->eng.size());
+    for (size_t d = 0; d < g->eng.size(); ++d) {
+        steps_b200_engine *e = g->eng[d];
+        DeviceGuard dg_;
+        CU_TRY(cudaSetDevice(e->device));
+        if (d == 0) {
+            CU_TRY(cudaMemcpyAsync(j.hx, e->d_x, 3 * n * rb, cudaMemcpyDeviceToHost, e->stream));  // every engine holds the full position replica
+            CU_TRY(cudaMemcpyAsync(j.hm, e->d_m, n * rb, cudaMemcpyDeviceToHost, e->stream));
+        }
+        const size_t off = 3 * (size_t)e->i_lo * rb, len = 3 * (size_t)(e->i_hi - e->i_lo) * rb;
+        CU_TRY(cudaMemcpyAsync(static_cast<char *>(j.hv) + off, static_cast<char *>(e->d_v) + off, len, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaEventCreateWithFlags(&done[d], cudaEventDisableTiming));
+        CU_TRY(cudaEventRecord(done[d], e->stream));
+    }
+    const std::string p(path);
+    j.err.clear();
+    j.running = true;
+    j.th = std::thread([&j, done, p, rb, n, h0_dimless, a, zero_velocities] {
+        for (cudaEvent_t ev : done) {
+            if (cudaEventSynchronize(ev) != cudaSuccess) j.err = "device copy failed";
+            cudaEventDestroy(ev);
+        }
+        if (!j.err.empty()) return;
+        j.err = rb == 8 ? snapshot_write_ascii<double>(p.c_str(), (const double *)j.hx, (const double *)j.hv, (const double *)j.hm, n, h0_dimless, a,
+                                                       zero_velocities, 0)
+                        : snapshot_write_ascii<float>(p.c_str(), (const float *)j.hx, (const float *)j.hv, (const float *)j.hm, n, h0_dimless, a,
+                                                      zero_velocities, 0);
+    });
+    return 0;
+}
+
 extern "C" int steps_b200_group_set_glass_making(steps_b200_group *g, int on) {
     if (!g) return fail("group is NULL");
     for (auto *e : g->eng)

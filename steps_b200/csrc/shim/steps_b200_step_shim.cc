@@ -101,6 +101,12 @@ extern "C" void steps_b200_shim_sync_host() {
     if (g_group && steps_b200_group_download(g_group, x, v, F)) fail("state download");
 }
 
+// the resident group (NULL before the first calculate_init_h()/step()): lets a caller that wants snapshots without stalling the GPUs replace
+//     write_ascii_snapshot(x, v);                                     (main.cc, OUTPUT_FORMAT == 0)
+// by  steps_b200_group_snapshot_ascii_async(steps_b200_shim_group(), filename, H0_dimless, a, glass_making);
+// -- same bytes in the file (tests/test_snapshot_io.py), written by a background thread while the next steps run
+extern "C" steps_b200_group *steps_b200_shim_group() { return g_group; }
+
 // drop the resident state (a new run in the same process; StePS itself never needs this)
 extern "C" void steps_b200_shim_reset() {
     if (g_group) steps_b200_group_destroy(g_group);

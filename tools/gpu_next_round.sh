@@ -44,6 +44,8 @@ STEPS_B200_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_reference_
 for cs in "c2 65536" "t3:64 32768" "s1r2nl:400000 32768"; do timeout 300 python tools/bench_ref_cuda.py $cs 2>&1 | tail -1 | cut -c1-600; done | tee $O/${TAG}_reference_cuda_bench.txt
 stamp "BASELINE configs[0] (C1: N=32768, force evaluation + 10 KDK steps) against the reference's own run (golden fixture)"
 STEPS_B200_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_c1_config.py -m gpu -q -s --timeout 100 2>&1 | grep -E "^C1|passed|failed|Error|assert" | cut -c1-260 | tee $O/${TAG}_c1_test.log
+stamp "asynchronous ASCII snapshot of the resident engines"
+STEPS_B200_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_snapshot.py -m gpu -q --timeout 100 2>&1 | tail -3 | tee $O/${TAG}_snapshot_test.log
 stamp "glass-making mode (glass_kernels.cuh, never run): engine vs the CPU port, drop-in glass build vs the reference's"
 STEPS_B200_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_glass.py -m gpu -q -s --timeout 120 > $O/${TAG}_glass_tests.log 2>&1
 echo "rc=$?" >> $O/${TAG}_glass_tests.log; grep -E "^glass|passed|failed|rc=|Error|assert" $O/${TAG}_glass_tests.log | cut -c1-260 | tail -12

@@ -42,7 +42,7 @@ def _coverage(n, nranks, ib):
 
 
 @pytest.mark.parametrize("nranks", [1, 2, 3, 4, 5, 6, 7, 8])
-@pytest.mark.parametrize("n,ib", [(20000, 768), (33333, 1024), (100000, 896), (16 * 768, 768)])
+@pytest.mark.parametrize("n,ib", [(20000, 768), (33333, 1024), (100000, 896), (16 * 768, 768), (8000, 384), (2744, 256), (5000, 128), (40000, 2048), (30000, 1536)])
 def test_every_interaction_exactly_once(n, nranks, ib):
     nb_total = (n + ib - 1) // ib
     if nb_total < 2 * nranks:

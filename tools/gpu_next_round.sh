@@ -53,6 +53,10 @@ measure)
     STEPS_B200_GEN_SYM=1 STEPS_B200_GEN_SYM_VARIANT=$v timeout 200 python tools/topo_bench.py t3:64,s1r2:200000 >> $O/${TAG}_generic_sweep.txt 2>&1
   done
   cut -c1-300 $O/${TAG}_generic_sweep.txt
+  stamp "measure: T^3 48^3 in lattice / random / cell-sorted particle order (tools/t3_wavefront_model.py predicts 1 : 1/6 : 1), one-sided then action-reaction"
+  timeout 300 python tools/topo_bench.py t3:48,t3:48:random,t3:48:cellsort > $O/${TAG}_t3_order.txt 2>&1
+  STEPS_B200_GEN_SYM=1 STEPS_B200_GEN_SYM_VARIANT=3 timeout 300 python tools/topo_bench.py t3:48,t3:48:random,t3:48:cellsort >> $O/${TAG}_t3_order.txt 2>&1
+  cut -c1-260 $O/${TAG}_t3_order.txt
   stamp "measure: the reference's own CUDA path timed against ours on the same rows"
   for cs in "c2 65536" "t3:64 32768" "s1r2nl:400000 32768"; do timeout 300 python tools/bench_ref_cuda.py $cs 2>&1 | tail -1 | cut -c1-600; done | tee $O/${TAG}_reference_cuda_bench.txt
   ;;

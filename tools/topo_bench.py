@@ -1,7 +1,7 @@
 """development aid: throughput of the pair kernels of the periodic topologies (and C1/C5 shapes) on one GPU.
 Input tables (T^3 Ewald, S^1xR^2 radial/Ewald) are built by the reference's own builders through oracle/_ref --
 this is a measuring tool, not product code.
-usage: topo_bench.py case[,case...]   cases: t3:<n_side>  s1r2nl:<N>  s1r2:<N>  r3f32:<N>  c1"""
+usage: topo_bench.py case[,case...]   cases: t3:<n_side>[:random|:cellsort]  s1r2nl:<N>  s1r2:<N>  r3f32:<N>  c1"""
 import json
 import os
 import sys
@@ -34,8 +34,23 @@ def run(case):
     kind, _, arg = case.partition(":")
     tb = 0.0
     if kind == "t3":
-        ns = int(arg)
-        c = ic.t3_lattice(ns, 20243, L=100.0, is_periodic=2, name=f"T^3 {ns}^3")
+        # t3:<n_side>[:random|:cellsort]  particle order: as generated (lattice, z fastest), shuffled, or shuffled then sorted by table cell
+        ns, _, order = arg.partition(":")
+        ns = int(ns)
+        c = ic.t3_lattice(ns, 20243, L=100.0, is_periodic=2, name=f"T^3 {ns}^3 {order or 'lattice'} order")
+        if order in ("random", "cellsort"):
+            rng = np.random.default_rng(7)
+            perm = rng.permutation(c.g.N)
+            if order == "cellsort":
+                ng = 63  # the table grid of IS_PERIODIC = 2
+                cell = np.floor(c.x.reshape(-1, 3)[perm] / (100.0 / ng)).astype(np.int64) % ng
+                perm = perm[np.argsort((cell[:, 0] * ng + cell[:, 1]) * ng + cell[:, 2], kind="stable")]
+            c.x[:] = c.x.reshape(-1, 3)[perm].reshape(-1)
+            c.v[:] = c.v.reshape(-1, 3)[perm].reshape(-1)
+            c.g.M = np.ascontiguousarray(c.g.M[perm])
+            c.g.SOFT_LENGTH = np.ascontiguousarray(c.g.SOFT_LENGTH[perm])
+        elif order:
+            raise SystemExit(f"unknown particle order {order}")
         tb = tables(c.g)
         evals = 1
     elif kind == "s1r2nl":

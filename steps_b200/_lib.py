@@ -107,6 +107,10 @@ SYMBOLS = {
     "steps_b200_snapshot_ascii_host": (_I, [C.c_char_p, _VP, _VP, _VP, _I, _I, _D, _D, _I, _I]),
     "steps_b200_group_snapshot_ascii_async": (_I, [_VP, C.c_char_p, _D, _D, _I]),
     "steps_b200_group_snapshot_wait": (_I, [_VP]),
+    "steps_b200_spatial_order": (_I, [_VP, _I, _I, _I, _PI]),
+    "steps_b200_permute": (_I, [_VP, _VP, _PI, _I, _I, _I, _I]),
+    "steps_b200_group_set_spatial_order": (_I, [_VP, _I]),
+    "steps_b200_group_permutation": (_I, [_VP, _PI]),
     "steps_b200_group_glass_stats": (_I, [_VP, _PD]),
     "steps_b200_engine_timings": (_I, [_VP, _PD, _PD]),
     "steps_b200_engine_pair_kernel_ms": (_I, [_VP, _PD]),

@@ -1691,6 +1691,10 @@ struct steps_b200_group {
     std::vector<steps_b200_engine *> eng;
     int n = 0, real_bytes = 8;
     SnapshotJob snap;  // asynchronous ASCII snapshot in flight (snapshot_io.h)
+    // spatial order (opt-in): the engines hold the particles sorted by cell; perm[k] = caller's index of the k-th resident particle
+    int order_ngrid = 0;
+    std::vector<int> perm;
+    std::vector<char> tmp[3];  // host staging for the permuted copies
 };
 
 namespace {
@@ -1773,6 +1777,25 @@ extern "C" steps_b200_engine *steps_b200_group_engine(steps_b200_group *g, int d
 
 extern "C" int steps_b200_group_upload(steps_b200_group *g, const void *x, const void *v, const void *M, const void *soft, const void *F) {
     if (!g) return fail("group is NULL");
+    if (g->order_ngrid > 0) {
+        // resident copy sorted by cell: build the permutation from these positions, upload gathered copies
+        if (!x || !M || !soft) return fail("x, M, soft must be non-NULL");
+        const int n = g->n, rb = g->real_bytes;
+        g->perm.resize((size_t)n);
+        if (steps_b200_spatial_order(x, n, rb, g->order_ngrid, g->perm.data())) return 1;
+        std::vector<char> px((size_t)3 * n * rb), pv(v ? (size_t)3 * n * rb : 0), pm((size_t)n * rb), ps((size_t)n * rb), pf(F ? (size_t)3 * n * rb : 0);
+        if (steps_b200_permute(x, px.data(), g->perm.data(), n, 3, rb, 0) || steps_b200_permute(M, pm.data(), g->perm.data(), n, 1, rb, 0) ||
+            steps_b200_permute(soft, ps.data(), g->perm.data(), n, 1, rb, 0) || (v && steps_b200_permute(v, pv.data(), g->perm.data(), n, 3, rb, 0)) ||
+            (F && steps_b200_permute(F, pf.data(), g->perm.data(), n, 3, rb, 0)))
+            return 1;
+        for (auto *e : g->eng) {
+            if (steps_b200_engine_upload(e, px.data(), v ? pv.data() : nullptr, pm.data(), ps.data())) return 1;
+            if (F && steps_b200_engine_upload_forces(e, pf.data())) return 1;
+        }
+        for (auto *e : g->eng)
+            if (steps_b200_engine_sync(e)) return 1;  // the staging vectors go out of scope below
+        return 0;
+    }
     for (auto *e : g->eng) {
         if (steps_b200_engine_upload(e, x, v, M, soft)) return 1;
         if (F && steps_b200_engine_upload_forces(e, F)) return 1;
@@ -1810,6 +1833,71 @@ extern "C" int steps_b200_group_kdk_step(steps_b200_group *g, double h, double a
 }
 
 // x: full (every engine holds the gathered replica -- taken from engine 0); v, F: each engine's owned rows
+// ------------------------------------------------------------------------------------------------ spatial order of the resident particles
+// The table-lookup topologies gather 64 table cells per pair at lane-dependent addresses; how many cache lines a warp-wide load
+// touches is decided by how close in space the 32 particles of a warp are (tools/t3_wavefront_model.py: 5 lines per load for particles
+// ordered by cell, 32 for particles in arbitrary order -- 6x in L1 wavefronts).  A caller's arrays come in whatever order the IC file has,
+// so a group can keep its resident copy sorted by cell: perm is built once at upload (bounding box of x, ngrid cells per axis, z fastest,
+// stable), uploads gather by it, downloads scatter back.  Forces change only by the order of summation.
+template <typename T>
+static void spatial_order_impl(const T *x, int n, int ngrid, int *perm) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = std::min(lo[k], (double)x[3 * (size_t)i + k]);
+            hi[k] = std::max(hi[k], (double)x[3 * (size_t)i + k]);
+        }
+    double inv[3];
+    for (int k = 0; k < 3; ++k) inv[k] = hi[k] > lo[k] ? ngrid / (hi[k] - lo[k]) : 0.0;
+    std::vector<long long> key((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        long long c[3];
+        for (int k = 0; k < 3; ++k) c[k] = std::min<long long>(ngrid - 1, std::max<long long>(0, (long long)(((double)x[3 * (size_t)i + k] - lo[k]) * inv[k])));
+        key[i] = (c[0] * ngrid + c[1]) * ngrid + c[2];
+    }
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    std::stable_sort(perm, perm + n, [&](int a, int b) { return key[a] < key[b]; });
+}
+
+extern "C" int steps_b200_spatial_order(const void *x, int n, int real_bytes, int ngrid, int *perm_out) {
+    if (!x || !perm_out || n <= 0 || ngrid < 1 || ngrid > 2048) return fail("bad arguments");
+    if (real_bytes == 8) spatial_order_impl<double>((const double *)x, n, ngrid, perm_out);
+    else if (real_bytes == 4) spatial_order_impl<float>((const float *)x, n, ngrid, perm_out);
+    else return fail("real_bytes must be 8 or 4");
+    return 0;
+}
+
+// dst[k] = src[perm[k]] (gather) or dst[perm[k]] = src[k] (scatter), rows of `width` elements of elem_bytes each
+extern "C" int steps_b200_permute(const void *src, void *dst, const int *perm, int n, int width, int elem_bytes, int scatter) {
+    if (!src || !dst || !perm || n < 0 || width < 1 || elem_bytes < 1 || src == dst) return fail("bad arguments");
+    const size_t row = (size_t)width * elem_bytes;
+    const char *s = static_cast<const char *>(src);
+    char *d = static_cast<char *>(dst);
+    for (int k = 0; k < n; ++k) {
+        if (perm[k] < 0 || perm[k] >= n) return fail("perm is not a permutation of [0, n)");
+        if (scatter) memcpy(d + (size_t)perm[k] * row, s + (size_t)k * row, row);
+        else memcpy(d + (size_t)k * row, s + (size_t)perm[k] * row, row);
+    }
+    return 0;
+}
+
+extern "C" int steps_b200_group_set_spatial_order(steps_b200_group *g, int ngrid) {
+    if (!g) return fail("group is NULL");
+    if (ngrid < 0 || ngrid > 2048) return fail("ngrid out of range");
+    for (auto *e : g->eng)
+        if (e->have_state) return fail("set_spatial_order must precede upload");
+    g->order_ngrid = ngrid;
+    g->perm.clear();
+    return 0;
+}
+
+extern "C" int steps_b200_group_permutation(steps_b200_group *g, int *perm_out) {
+    if (!g || !perm_out) return fail("group or output is NULL");
+    if (g->perm.empty()) return fail("no spatial order in force (set_spatial_order + upload)");
+    memcpy(perm_out, g->perm.data(), g->perm.size() * sizeof(int));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ snapshots (ASCII)
 extern "C" int steps_b200_snapshot_ascii_host(const char *path, const void *x, const void *v, const void *M, int n, int real_bytes,
                                               double h0_dimless, double a, int zero_velocities, int nthreads) {
@@ -1874,15 +1962,27 @@ extern "C" int steps_b200_group_snapshot_ascii_async(steps_b200_group *g, const 
     const std::string p(path);
     j.err.clear();
     j.running = true;
-    j.th = std::thread([&j, done, p, rb, n, h0_dimless, a, zero_velocities] {
+    const std::vector<int> perm = g->perm;  // resident order -> caller's order (empty: identical)
+    j.th = std::thread([&j, done, p, rb, n, h0_dimless, a, zero_velocities, perm] {
         for (cudaEvent_t ev : done) {
             if (cudaEventSynchronize(ev) != cudaSuccess) j.err = "device copy failed";
             cudaEventDestroy(ev);
         }
         if (!j.err.empty()) return;
-        j.err = rb == 8 ? snapshot_write_ascii<double>(p.c_str(), (const double *)j.hx, (const double *)j.hv, (const double *)j.hm, n, h0_dimless, a,
+        const void *sx = j.hx, *sv = j.hv, *sm = j.hm;
+        std::vector<char> ox, ov, om;
+        if (!perm.empty()) {
+            ox.resize(3 * n * rb); ov.resize(3 * n * rb); om.resize(n * rb);
+            if (steps_b200_permute(j.hx, ox.data(), perm.data(), (int)n, 3, (int)rb, 1) || steps_b200_permute(j.hv, ov.data(), perm.data(), (int)n, 3, (int)rb, 1) ||
+                steps_b200_permute(j.hm, om.data(), perm.data(), (int)n, 1, (int)rb, 1)) {
+                j.err = "permutation failed";
+                return;
+            }
+            sx = ox.data(); sv = ov.data(); sm = om.data();
+        }
+        j.err = rb == 8 ? snapshot_write_ascii<double>(p.c_str(), (const double *)sx, (const double *)sv, (const double *)sm, n, h0_dimless, a,
                                                        zero_velocities, 0)
-                        : snapshot_write_ascii<float>(p.c_str(), (const float *)j.hx, (const float *)j.hv, (const float *)j.hm, n, h0_dimless, a,
+                        : snapshot_write_ascii<float>(p.c_str(), (const float *)sx, (const float *)sv, (const float *)sm, n, h0_dimless, a,
                                                       zero_velocities, 0);
     });
     return 0;
@@ -1901,8 +2001,29 @@ extern "C" int steps_b200_group_glass_stats(steps_b200_group *g, double *out8) {
     return steps_b200_engine_glass_stats(g->eng[0], out8);
 }
 
+static int group_download_raw(steps_b200_group *g, void *x, void *v, void *F);
+
 extern "C" int steps_b200_group_download(steps_b200_group *g, void *x, void *v, void *F) {
     if (!g) return fail("group is NULL");
+    if (!g->perm.empty()) {
+        // resident order -> caller's order
+        const int n = g->n, rb = g->real_bytes;
+        void *out[3] = {x, v, F};
+        void *raw[3] = {nullptr, nullptr, nullptr};
+        for (int k = 0; k < 3; ++k)
+            if (out[k]) {
+                g->tmp[k].resize((size_t)3 * n * rb);
+                raw[k] = g->tmp[k].data();
+            }
+        if (group_download_raw(g, raw[0], raw[1], raw[2])) return 1;
+        for (int k = 0; k < 3; ++k)
+            if (out[k] && steps_b200_permute(raw[k], out[k], g->perm.data(), n, 3, rb, 1)) return 1;
+        return 0;
+    }
+    return group_download_raw(g, x, v, F);
+}
+
+static int group_download_raw(steps_b200_group *g, void *x, void *v, void *F) {
     const size_t rb = g->real_bytes;
     for (size_t d = 0; d < g->eng.size(); ++d) {
         steps_b200_engine *e = g->eng[d];

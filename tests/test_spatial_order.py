@@ -1,0 +1,135 @@
+"""Spatial order of the resident particles (steps_b200_spatial_order / steps_b200_permute / steps_b200_group_set_spatial_order).
+CPU tier: the host-only helpers.  GPU tier (gated: added after round 1's GPU budget was spent): a group that keeps its resident copy
+sorted by cell returns, in the caller's order, the same forces and the same KDK trajectory as a group that does not."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from steps_b200 import _lib, ic
+
+PI = C.POINTER(C.c_int)
+
+
+def order(x, ngrid):
+    lib = _lib.load()
+    x = np.ascontiguousarray(x)
+    n = x.size // 3
+    perm = np.empty(n, dtype=np.int32)
+    _lib.check(lib.steps_b200_spatial_order(x.ctypes.data, n, x.dtype.itemsize, ngrid, perm.ctypes.data_as(PI)))
+    return perm
+
+
+def permute(src, perm, width, scatter):
+    lib = _lib.load()
+    src = np.ascontiguousarray(src)
+    dst = np.empty_like(src)
+    _lib.check(lib.steps_b200_permute(src.ctypes.data, dst.ctypes.data, perm.ctypes.data_as(PI), perm.size, width, src.dtype.itemsize, scatter))
+    return dst
+
+
+@pytest.mark.parametrize("REAL", [np.float64, np.float32])
+def test_spatial_order_sorts_by_cell_z_fastest_and_is_stable(REAL):
+    rng = np.random.default_rng(3)
+    n, ng = 5000, 7
+    x = rng.random((n, 3)).astype(REAL) * REAL(30.0) - REAL(4.0)
+    perm = order(x.reshape(-1), ng)
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    lo, hi = x.astype(np.float64).min(axis=0), x.astype(np.float64).max(axis=0)
+    cell = np.minimum(ng - 1, ((x.astype(np.float64) - lo) * (ng / (hi - lo))).astype(np.int64))
+    key = (cell[:, 0] * ng + cell[:, 1]) * ng + cell[:, 2]
+    ks = key[perm]
+    assert np.all(np.diff(ks) >= 0)                                  # sorted by cell, z fastest
+    same = np.diff(ks) == 0
+    assert np.all(np.diff(perm)[same] > 0)                           # stable inside a cell
+    assert np.array_equal(perm, np.argsort(key, kind="stable"))
+
+
+def test_permute_gather_and_scatter_are_inverse():
+    rng = np.random.default_rng(4)
+    n = 1234
+    perm = rng.permutation(n).astype(np.int32)
+    for width, dt in ((3, np.float64), (1, np.float64), (3, np.float32), (1, np.float32)):
+        a = rng.random(n * width).astype(dt)
+        g = permute(a, perm, width, 0)
+        assert np.array_equal(g.reshape(n, width), a.reshape(n, width)[perm])
+        assert np.array_equal(permute(g, perm, width, 1), a)
+
+
+def test_bad_arguments_fail_loudly():
+    lib = _lib.load()
+    x = np.zeros(6)
+    perm = np.array([0, 5], dtype=np.int32)
+    assert lib.steps_b200_permute(x.ctypes.data, np.empty(6).ctypes.data, perm.ctypes.data_as(PI), 2, 3, 8, 0) != 0
+    assert b"not a permutation" in lib.steps_b200_last_error()
+    assert lib.steps_b200_spatial_order(None, 0, 8, 4, None) != 0
+
+
+def test_degenerate_extent_is_handled():
+    x = np.zeros(30)
+    x[2::3] = np.arange(10)[::-1]  # all particles on the z axis, descending
+    perm = order(x, 4)
+    assert np.array_equal(np.sort(perm), np.arange(10))
+    assert np.all(np.diff(x[2::3][perm] // 2.2500001) >= 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("STEPS_B200_EXPERIMENTAL") != "1", reason="added after round 1's GPU budget was spent: set STEPS_B200_EXPERIMENTAL=1")
+@pytest.mark.parametrize("case", ["r3", "t3"])
+def test_group_in_spatial_order_gives_the_callers_order_back(case):
+    import steps_b200 as sb
+    from oracle import pyref
+
+    if case == "t3":
+        if not pyref.available("t3_f64"):
+            pytest.skip("T^3 table needs oracle/_ref")
+        c = ic.t3_lattice(12, 61, L=30.0, is_periodic=2)
+        r = pyref.Reference("t3_f64")
+        r.configure(c.g, 400)
+        r.build_tables()
+        r.export_tables(c.g)
+    else:
+        c = ic.random_sphere(6000, 19)
+    g = c.g
+    rng = np.random.default_rng(5)
+    shuffle = rng.permutation(g.N)  # a caller whose arrays are in no particular order
+    x = np.ascontiguousarray(c.x.reshape(-1, 3)[shuffle].reshape(-1))
+    v = np.ascontiguousarray(c.v.reshape(-1, 3)[shuffle].reshape(-1))
+    g.M = np.ascontiguousarray(g.M[shuffle])
+    g.SOFT_LENGTH = np.ascontiguousarray(g.SOFT_LENGTH[shuffle])
+    lib = _lib.load()
+    out = []
+    for ngrid in (0, 16):
+        grp = C.c_void_p()
+        p = g.cparams()
+        _lib.check(lib.steps_b200_group_create(C.byref(grp), C.byref(p), 8, 1, 0))
+        _lib.check(lib.steps_b200_group_set_spatial_order(grp, ngrid))
+        _lib.check(lib.steps_b200_group_upload(grp, x.ctypes.data, v.ctypes.data, g.M.ctypes.data, g.SOFT_LENGTH.ctypes.data, None))
+        _lib.check(lib.steps_b200_group_forces(grp))
+        a0 = g.a_start
+        H0 = sb.CALCULATE_Hubble_param(g, a0)
+        em = C.c_double()
+        _lib.check(lib.steps_b200_group_init_errmax(grp, a0, H0, C.byref(em)))
+        h = (2 * g.ACC_PARAM / em.value) ** 0.5
+        a, H, errs = a0, H0, [em.value]
+        for _ in range(3):
+            an = sb.friedmann_solver_step(g, a, h)
+            Hn = sb.CALCULATE_Hubble_param(g, an)
+            _lib.check(lib.steps_b200_group_kdk_step(grp, h, a, H, an, Hn, C.byref(em)))
+            a, H = an, Hn
+            errs.append(em.value)
+        x1, v1, F1 = (np.empty(3 * g.N) for _ in range(3))
+        _lib.check(lib.steps_b200_group_download(grp, x1.ctypes.data, v1.ctypes.data, F1.ctypes.data))
+        if ngrid:
+            perm = np.empty(g.N, dtype=np.int32)
+            _lib.check(lib.steps_b200_group_permutation(grp, perm.ctypes.data_as(PI)))
+            assert np.array_equal(np.sort(perm), np.arange(g.N))
+        lib.steps_b200_group_destroy(grp)
+        out.append((x1, v1, F1, errs))
+    (xa, va, Fa, ea), (xb, vb, Fb, eb) = out
+    scale = max(g.Rsim, g.L)
+    print(f"{case}: spatial order on/off: max |dx|/scale {np.abs(xa - xb).max() / scale:.2e}, max |dF|/max|F| {np.abs(Fa - Fb).max() / np.abs(Fa).max():.2e}")
+    assert np.allclose(ea, eb, rtol=1e-10)
+    assert np.abs(xa - xb).max() / scale < 1e-12
+    assert np.abs(Fa - Fb).max() / np.abs(Fa).max() < 1e-11

@@ -35,6 +35,8 @@ verify)
   gated snapshot_test "snapshot" tests/test_gpu_snapshot.py
   stamp "verify: BASELINE configs[0] (C1) against the reference's own run"
   gated c1_test "^C1" tests/test_c1_config.py
+  stamp "verify: group in spatial order returns the caller's order"
+  gated spatial_order_test "spatial order" tests/test_spatial_order.py
   stamp "verify: the drop-in executable StePS_b200 against the reference executable (same parameter file and ASCII IC)"
   gated whole_binary_test "whole binary" tests/test_whole_binary.py
   stamp "verify: ours against the reference's own CUDA kernels (forces_cuda.cu for sm_100a)"

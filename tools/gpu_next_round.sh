@@ -59,6 +59,9 @@ measure)
   timeout 300 python tools/topo_bench.py t3:48,t3:48:random,t3:48:cellsort > $O/${TAG}_t3_order.txt 2>&1
   STEPS_B200_GEN_SYM=1 STEPS_B200_GEN_SYM_VARIANT=3 timeout 300 python tools/topo_bench.py t3:48,t3:48:random,t3:48:cellsort >> $O/${TAG}_t3_order.txt 2>&1
   cut -c1-260 $O/${TAG}_t3_order.txt
+  stamp "measure: C2 with a 48 GB j-side row buffer (3 passes instead of 8; tools/pass_model.py: 0.988 -> 0.995 of ideal)"
+  STEPS_B200_SYM_GPART_MB=49152 timeout 200 python bench.py --steps 2 --warmup 3 --no-cpu > $O/${TAG}_bench_c2_gpart48g.json 2> $O/${TAG}_bench_c2_gpart48g.err
+  cut -c1-200 $O/${TAG}_bench_c2_gpart48g.json
   stamp "measure: the reference's own CUDA path timed against ours on the same rows"
   for cs in "c2 65536" "t3:64 32768" "s1r2nl:400000 32768"; do timeout 300 python tools/bench_ref_cuda.py $cs 2>&1 | tail -1 | cut -c1-600; done | tee $O/${TAG}_reference_cuda_bench.txt
   ;;

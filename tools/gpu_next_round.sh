@@ -7,6 +7,7 @@
 #            kernels timed against ours on the same rows                                                                   (~5 min)
 #   profile  ncu --set full: T^3 one-sided and action-reaction kernels (L1 wavefronts per load), FP32 action-reaction kernel  (~4 min)
 #   final    full regression + bench on the same box                                                                       (~2 min)
+#   c5full   (only when named) one KDK step at the full C5 size, N = 16.7M FP32                                            (~8 min)
 TAG=${1:-r2a}
 shift
 PARTS=${*:-verify measure profile final}
@@ -84,6 +85,12 @@ final)
   stamp "final: bench"
   timeout 300 python bench.py --steps 3 --warmup 3 > $O/${TAG}_bench_c2_1gpu.json 2> $O/${TAG}_bench_c2_1gpu.err
   cut -c1-260 $O/${TAG}_bench_c2_1gpu.json; tail -2 $O/${TAG}_bench_c2_1gpu.err
+  ;;
+c5full)
+  # not in the default list: BASELINE configs[4] at its real size (N = 16 777 216 FP32, 2.8e14 interactions, about 100 s per evaluation)
+  stamp "c5full: one timed KDK step at the full C5 size (warm-up 1: a development number, not a bench line)"
+  timeout 1500 python bench.py --config c5 --steps 1 --warmup 1 --no-cpu > $O/${TAG}_bench_c5_full.json 2> $O/${TAG}_bench_c5_full.err
+  cut -c1-300 $O/${TAG}_bench_c5_full.json; tail -3 $O/${TAG}_bench_c5_full.err
   ;;
 *) echo "unknown part $part";;
 esac; done

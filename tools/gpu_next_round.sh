@@ -7,6 +7,7 @@
 #            kernels timed against ours on the same rows                                                                   (~5 min)
 #   profile  ncu --set full: T^3 one-sided and action-reaction kernels (L1 wavefronts per load), FP32 action-reaction kernel  (~4 min)
 #   final    full regression + bench on the same box                                                                       (~2 min)
+#   c3full, c4full (only when named) pair-kernel throughput at the full C3 / C4 sizes, one-sided then action-reaction    (~15 / ~8 min)
 #   c5full   (only when named) one KDK step at the full C5 size, N = 16.7M FP32                                            (~8 min)
 TAG=${1:-r2a}
 shift
@@ -91,6 +92,18 @@ c5full)
   stamp "c5full: one timed KDK step at the full C5 size (warm-up 1: a development number, not a bench line)"
   timeout 1500 python bench.py --config c5 --steps 1 --warmup 1 --no-cpu > $O/${TAG}_bench_c5_full.json 2> $O/${TAG}_bench_c5_full.err
   cut -c1-300 $O/${TAG}_bench_c5_full.json; tail -3 $O/${TAG}_bench_c5_full.err
+  ;;
+c4full)
+  # not in the default list: BASELINE configs[3] at its real size (S^1xR^2 NOLOOKUP, N = 4 194 304), one-sided then action-reaction
+  stamp "c4full: pair-kernel throughput at the full C4 size"
+  timeout 900 python tools/topo_bench.py s1r2nl:4194304 2>&1 | tail -1 | cut -c1-400 | tee $O/${TAG}_c4_full.txt
+  STEPS_B200_S1R2_SYM=1 timeout 900 python tools/topo_bench.py s1r2nl:4194304 2>&1 | tail -1 | cut -c1-400 | tee -a $O/${TAG}_c4_full.txt
+  ;;
+c3full)
+  # not in the default list: BASELINE configs[2] at its real size (T^3, 128^3), one-sided then action-reaction (lean arithmetic)
+  stamp "c3full: pair-kernel throughput at the full C3 size"
+  timeout 1500 python tools/topo_bench.py t3:128 2>&1 | tail -1 | cut -c1-400 | tee $O/${TAG}_c3_full.txt
+  STEPS_B200_GEN_SYM=1 STEPS_B200_GEN_SYM_VARIANT=3 timeout 1500 python tools/topo_bench.py t3:128 2>&1 | tail -1 | cut -c1-400 | tee -a $O/${TAG}_c3_full.txt
   ;;
 *) echo "unknown part $part";;
 esac; done

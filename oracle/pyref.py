@@ -15,6 +15,15 @@ VARIANT = {  # (topology, real_bytes) -> variant name
     (0, 8): "r3_f64", (0, 4): "r3_f32", (1, 8): "t3_f64", (1, 4): "t3_f32",
     (2, 8): "s1r2_f64", (3, 8): "s1r2nl_f64", (3, 4): "s1r2nl_f32",
 }
+# the S^1xR^2 lookup build exists once per EWALD_INTERPOLATION_ORDER (a compile-time macro of the reference): 4 = TSC, 2 = CIC, 0 = NGP
+S1R2_ORDER_VARIANT = {4: "s1r2_f64", 2: "s1r2cic_f64", 0: "s1r2ngp_f64"}
+
+
+def variant_for(g) -> str:
+    rb = 8 if g.REAL == np.float64 else 4
+    if g.topology == 2 and rb == 8:
+        return S1R2_ORDER_VARIANT[int(g.EWALD_INTERPOLATION_ORDER)]
+    return VARIANT[(g.topology, rb)]
 
 
 class SrefConfig(C.Structure):
@@ -67,7 +76,7 @@ class Reference:
 
     @classmethod
     def for_globals(cls, g) -> "Reference":
-        return cls(VARIANT[(g.topology, 8 if g.REAL == np.float64 else 4)])
+        return cls(variant_for(g))
 
     def configure(self, g, radial_accuracy: int = 7500) -> None:
         """copy a steps_b200.api.Globals into the reference's globals and run its own setup"""

@@ -227,6 +227,7 @@ struct steps_b200_engine {
     TopoParams tp{};
     // action-reaction (symmetric) R^3 FP64 path, pair_r3_sym.cuh
     bool sym = false;            // requested (STEPS_B200_SYM / steps_b200_engine_set_symmetric) and applicable
+    int sym_request = -1;        // the caller's explicit choice: -1 = none (environment default), 0 = one-sided, 1 = action-reaction
     int sym_ib = 0;              // i-block size of the symmetric kernel shape
     std::vector<SymRule> h_rules;  // one per local i-block of [i_lo, i_hi)
     SymRule *d_rules = nullptr;
@@ -424,18 +425,18 @@ int s1r2_sym_variant() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("STEPS_B200_S1R2_SYM_VARIANT");
-        v = s ? atoi(s) : 0;
-        if (v < 0 || v >= N_S1R2_SYM_VARIANTS) v = 0;
+        v = s ? atoi(s) : 2;  // fastest of the round-2 sweep (profiles/r2a_s1r2_sweep.txt: 3.89e11 pairs/s at N = 400k, 7 images)
+        if (v < 0 || v >= N_S1R2_SYM_VARIANTS) v = 2;
     }
     return v;
 }
-// OPT-IN (STEPS_B200_S1R2_SYM=1, or an explicit steps_b200_engine_set_symmetric(e, 1)) until all of tests/test_gpu_s1r2_sym.py has run on a
-// GPU (12 of 16 tests green and 1.7x the one-sided kernel in the last seconds of round 1's GPU budget).
+// On by default since round 2 (all 16 tests of tests/test_gpu_s1r2_sym.py green on a B200, 1.65-1.77x the one-sided kernel,
+// profiles/r2a_*); STEPS_B200_S1R2_SYM=0 or STEPS_B200_SYM=0 keeps the one-sided image-sum kernel.
 bool s1r2_sym_env_default() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("STEPS_B200_S1R2_SYM");
-        v = (s && atoi(s) != 0) ? 1 : 0;
+        v = (s && atoi(s) == 0) ? 0 : 1;
     }
     return v == 1 && sym_env_default();
 }
@@ -455,17 +456,18 @@ int gen_sym_variant() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("STEPS_B200_GEN_SYM_VARIANT");
-        v = s ? atoi(s) : 0;
-        if (v < 0 || v >= N_GEN_SYM_VARIANTS) v = 0;
+        v = s ? atoi(s) : 5;  // fastest of the round-2 sweep for both lookup topologies (profiles/r2a_generic_sweep.txt)
+        if (v < 0 || v >= N_GEN_SYM_VARIANTS) v = 5;
     }
     return v;
 }
-// OPT-IN (STEPS_B200_GEN_SYM=1 or an explicit steps_b200_engine_set_symmetric(e, 1)): not run on a GPU yet.
+// On by default since round 2 (tests/test_gpu_generic_sym.py green on a B200 with the exact and the lean arithmetic; T^3 64^3:
+// 2.5e10 against 9.9e9 pairs/s one-sided); STEPS_B200_GEN_SYM=0 or STEPS_B200_SYM=0 keeps the one-sided kernel.
 bool gen_sym_env_default() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("STEPS_B200_GEN_SYM");
-        v = (s && atoi(s) != 0) ? 1 : 0;
+        v = (s && atoi(s) == 0) ? 0 : 1;
     }
     return v == 1 && sym_env_default();
 }
@@ -1120,6 +1122,7 @@ extern "C" int steps_b200_engine_set_symmetric(steps_b200_engine *e, int on) {
     if (e->comm) return fail("set_symmetric must precede comm_init");
     DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
+    e->sym_request = on != 0 ? 1 : 0;  // remembered: comm_init re-partitions and must not fall back to the environment default
     return setup_partition(e, on != 0);
 }
 
@@ -1195,7 +1198,7 @@ extern "C" int steps_b200_engine_comm_init(steps_b200_engine *e, const void *id1
     e->nranks = nranks;
     DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
-    if (setup_partition(e, e->sym || sym_default_for(e))) return 1;
+    if (setup_partition(e, e->sym_request >= 0 ? e->sym_request == 1 : sym_default_for(e))) return 1;
     if (nranks == 1) return 0;
     if (nccl_load()) return 1;
     ncclUniqueId id;

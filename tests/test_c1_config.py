@@ -44,7 +44,6 @@ def test_c1_port_initial_forces_on_sampled_rows(c1):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("STEPS_B200_EXPERIMENTAL") != "1", reason="added after round 1's GPU budget was spent: set STEPS_B200_EXPERIMENTAL=1")
 def test_c1_force_evaluation_and_ten_kdk_steps_on_the_gpu(c1):
     import steps_b200 as sb
 

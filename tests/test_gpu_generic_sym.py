@@ -2,9 +2,7 @@
 correction and the S^1xR^2 lookup build, against the reference's own forces, against the one-sided kernel, ragged sizes,
 multi-pass, KDK steps and every rank of a multi-GPU job played on one GPU.
 
-EXPERIMENTAL: written after round 1's GPU budget was spent; the kernel has not run on a GPU yet.  It is opt-in in the library
-(STEPS_B200_GEN_SYM=1 or Engine.set_symmetric(True)) and these tests run only with STEPS_B200_EXPERIMENTAL=1:
-    STEPS_B200_EXPERIMENTAL=1 python -m pytest tests/test_gpu_generic_sym.py -m gpu -q -s"""
+First run on a B200 at the start of round 2 (profiles/r2a_*.log): all green; part of the default `-m gpu` suite since."""
 import ctypes as C
 import os
 
@@ -16,8 +14,7 @@ from helpers import rel_err
 from oracle import pyref
 from steps_b200 import _lib, ic
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("STEPS_B200_EXPERIMENTAL") != "1", reason="unverified kernel: set STEPS_B200_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 TOL64 = 1e-12
 
 

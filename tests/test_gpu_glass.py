@@ -2,9 +2,7 @@
 -DGLASS_MAKING step(), step.cc:107-148, :254-303) against the CPU port pinned to the reference's glass build (tests/test_glass.py),
 in both precisions and with every rank of a multi-GPU job played on one GPU.
 
-EXPERIMENTAL: written after round 1's GPU budget was spent; the kernels have not run on a GPU yet, the mode is opt-in
-(Engine.set_glass_making) and these tests run only with STEPS_B200_EXPERIMENTAL=1:
-    STEPS_B200_EXPERIMENTAL=1 python -m pytest tests/test_gpu_glass.py -m gpu -q -s"""
+First run on a B200 at the start of round 2 (profiles/r2a_*.log): all green; part of the default `-m gpu` suite since."""
 import os
 
 import numpy as np
@@ -16,8 +14,7 @@ from oracle import pyport, pyref
 from steps_b200 import ic
 from test_glass import port_glass_run
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("STEPS_B200_EXPERIMENTAL") != "1", reason="unverified kernels: set STEPS_B200_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 KEYS = ("F_mean", "Fmax", "A_mean", "A_max", "dmean", "dmax", "V_mean", "V_max")
 
 

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 FORCE_CASES = ["r3_f64_comoving", "r3_f64_noncomoving", "r3_f64_nocosmo", "r3_f32_comoving", "r3_f64_zoom", "t3_f64_quasi",
                "t3_f64_ewald", "t3_f32_ewald", "s1r2nl_f64_images", "s1r2nl_f64_quasi", "s1r2nl_f32_images", "s1r2_f64_lookup",
-               "s1r2_f64_lookup_quasi"]
+               "s1r2_f64_lookup_quasi", "s1r2_f64_lookup_cic", "s1r2_f64_lookup_ngp"]
 TOL64, TOL32 = 1e-12, 1e-5
 
 
@@ -197,7 +197,7 @@ def test_resident_engine_matches_stateless_and_upload_x():
     eng.close()
 
 
-@pytest.mark.parametrize("topo_case", ["t3", "s1r2nl", "s1r2"])
+@pytest.mark.parametrize("topo_case", ["t3", "s1r2nl", "s1r2", "s1r2_cic", "s1r2_ngp"])
 def test_periodic_topologies_vs_oracle_midsize(topo_case):
     if topo_case == "t3":
         c = ic.t3_lattice(14, 61, L=30.0, is_periodic=2)
@@ -207,10 +207,12 @@ def test_periodic_topologies_vs_oracle_midsize(topo_case):
         c = ic.s1r2_cylinder(3000, 24, 80, 62, lookup=False, is_periodic=2, L=20.0, r_sim=60.0, d_s=10.0, r_crit=15.0)
     else:
         c = ic.s1r2_cylinder(3000, 24, 80, 63, lookup=True, is_periodic=2, L=20.0, r_sim=30.0, d_s=8.0, r_crit=10.0)
+        # the lookup build once per EWALD_INTERPOLATION_ORDER: TSC (4), CIC (2, the reference template's default), NGP (0)
+        c.g.EWALD_INTERPOLATION_ORDER = {"s1r2": 4, "s1r2_cic": 2, "s1r2_ngp": 0}[topo_case]
     g = c.g
-    key = (g.topology, 8)
-    if pyref.available(pyref.VARIANT[key]):
-        r = pyref.Reference(pyref.VARIANT[key])
+    variant = pyref.variant_for(g)
+    if pyref.available(variant):
+        r = pyref.Reference(variant)
         r.configure(g, 400)
         r.build_tables()
         r.export_tables(g)
@@ -426,7 +428,8 @@ def test_full_size_c2_properties():
 
 # ---------------------------------------------------------------- the drop-in boundary
 SHIM_FORCE_CASES = [("r3_f64_comoving", "r3_f64"), ("r3_f32_comoving", "r3_f32"), ("r3_f64_zoom", "r3_f64"), ("t3_f64_ewald", "t3_f64"),
-                    ("s1r2nl_f64_images", "s1r2nl_f64"), ("s1r2_f64_lookup", "s1r2_f64")]
+                    ("s1r2nl_f64_images", "s1r2nl_f64"), ("s1r2_f64_lookup", "s1r2_f64"),
+                    ("s1r2_f64_lookup_cic", "s1r2cic_f64")]
 
 
 @pytest.mark.parametrize("name,variant", SHIM_FORCE_CASES)

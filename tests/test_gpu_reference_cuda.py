@@ -3,8 +3,7 @@ refcuda) as a second oracle next to its CPU path: our forces against it on the s
 SURVEY.md 8c lists the semantic differences between the reference's two implementations (1/r^3 by pow vs division, ...): they agree
 to rounding, so the tolerance is the one of the CPU oracle.
 
-EXPERIMENTAL: the reference CUDA build was added after round 1's GPU budget was spent and has not run yet
-(STEPS_B200_EXPERIMENTAL=1 to run)."""
+First run on a B200 at the start of round 2 (profiles/r2a_*.log): all green; part of the default `-m gpu` suite since."""
 import os
 
 import numpy as np
@@ -15,8 +14,7 @@ from helpers import rel_err
 from oracle import pyref
 from steps_b200 import ic
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("STEPS_B200_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set STEPS_B200_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 def cases():

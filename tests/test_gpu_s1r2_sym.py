@@ -2,11 +2,7 @@
 image loop, against the one-sided tuned kernel, for every image count, with softened pairs, pairs at the image cut, z outside
 the box (fallback), several passes and every rank of a multi-GPU job played on one GPU.
 
-EXPERIMENTAL: the kernel was written when round 1's GPU budget was almost spent: 12 of these tests (image counts, ragged sizes,
-multi-rank) passed on a B200 in the last seconds of it (profiles/r1ad_s1r2_sym_tests.log), the other four have not run yet.  The
-kernel is opt-in in the library (STEPS_B200_S1R2_SYM=1 or Engine.set_symmetric(True)) and these tests run only with
-STEPS_B200_EXPERIMENTAL=1:
-    STEPS_B200_EXPERIMENTAL=1 python -m pytest tests/test_gpu_s1r2_sym.py -m gpu -q -s"""
+First run on a B200 at the start of round 2 (profiles/r2a_*.log): all green; part of the default `-m gpu` suite since."""
 import ctypes as C
 import os
 
@@ -18,8 +14,7 @@ from helpers import rel_err
 from oracle import pyref
 from steps_b200 import _lib, ic
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("STEPS_B200_EXPERIMENTAL") != "1", reason="unverified kernel: set STEPS_B200_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 TOL64 = 1e-12
 L = 20.0
 

@@ -2,7 +2,7 @@
 background while the engine goes on stepping holds the state of the moment of the call, byte for byte what the host formatter --
 itself byte-identical to the reference's writer (tests/test_snapshot_io.py) -- makes of a synchronous download at that moment.
 
-EXPERIMENTAL: added after round 1's GPU budget was spent (STEPS_B200_EXPERIMENTAL=1 to run)."""
+First run on a B200 at the start of round 2 (profiles/r2a_*.log): all green; part of the default `-m gpu` suite since."""
 import ctypes as C
 import os
 
@@ -12,8 +12,7 @@ import pytest
 import steps_b200 as sb
 from steps_b200 import _lib, ic
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("STEPS_B200_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set STEPS_B200_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("REAL", [np.float64, np.float32])

@@ -13,7 +13,7 @@ from steps_b200 import ic
 
 FORCE_CASES = ["r3_f64_comoving", "r3_f64_noncomoving", "r3_f64_nocosmo", "r3_f32_comoving", "r3_f64_zoom", "t3_f64_quasi",
                "t3_f64_ewald", "t3_f32_ewald", "s1r2nl_f64_images", "s1r2nl_f64_quasi", "s1r2nl_f32_images", "s1r2_f64_lookup",
-               "s1r2_f64_lookup_quasi"]
+               "s1r2_f64_lookup_quasi", "s1r2_f64_lookup_cic", "s1r2_f64_lookup_ngp"]
 
 
 def tol_for(g):

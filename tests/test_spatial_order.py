@@ -75,7 +75,6 @@ def test_degenerate_extent_is_handled():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("STEPS_B200_EXPERIMENTAL") != "1", reason="added after round 1's GPU budget was spent: set STEPS_B200_EXPERIMENTAL=1")
 @pytest.mark.parametrize("case", ["r3", "t3"])
 def test_group_in_spatial_order_gives_the_callers_order_back(case):
     import steps_b200 as sb

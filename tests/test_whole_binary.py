@@ -108,7 +108,6 @@ def test_dropin_binary_without_a_gpu_fails_loudly():
 
 @needs_binaries
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("STEPS_B200_EXPERIMENTAL") != "1", reason="added after round 1's GPU budget was spent: set STEPS_B200_EXPERIMENTAL=1")
 def test_dropin_binary_reproduces_the_reference_binary(tmp_path):
     d = str(tmp_path)
     c = write_case(d, n=2000, seed=9)

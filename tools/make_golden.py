@@ -106,9 +106,22 @@ def scalar_cases():
     print("scalars", w64[:4])
 
 
+def order_cases():
+    """S^1xR^2 lookup build with the other two interpolation orders (EWALD_INTERPOLATION_ORDER = 2 is the reference template's
+    default, Template-LinuxGCC-Makefile:35; 0 = NGP): forces_cuda.cu:188-283 / ewald_space.cc:803-960"""
+    kw = dict(L=20.0, r_sim=10.0, d_s=4.0, r_crit=3.0)
+    for tag, order, seed in (("cic", 2, 114), ("ngp", 0, 115)):
+        c = ic.s1r2_cylinder(320, 12, 20, seed, lookup=True, is_periodic=2, **kw)
+        c.g.EWALD_INTERPOLATION_ORDER = order
+        force_case(f"s1r2_f64_lookup_{tag}", c)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "orders" in sys.argv[1:]:
+        return order_cases()
     scalar_cases()
+    order_cases()
     force_case("r3_f64_comoving", ic.random_sphere(300, 101))
     force_case("r3_f64_noncomoving", ic.random_sphere(257, 102, comoving=0))
     force_case("r3_f64_nocosmo", ic.random_sphere(129, 103, cosmology=0))

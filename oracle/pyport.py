@@ -81,7 +81,8 @@ def forces(g, x, id_min, id_max, nthreads=0) -> np.ndarray:
 
 
 def force_norms(g, x, id_min, id_max, nthreads=0) -> np.ndarray:
-    """sum_j |f_ij| per i (float64 R^3): the scale of the reference's own summation noise"""
+    """sum_j |f_ij| per i (float64; nearest image in the periodic topologies): the scale of the reference's own summation noise
+    """
     lib, keep = load(), []
     p = _params(g, nthreads, keep)
     x = np.ascontiguousarray(x, dtype=np.float64)

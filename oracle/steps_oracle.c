@@ -30,6 +30,12 @@ void oracle_force_norms_f64(const oracle_params *p, const double *x, const doubl
         double s = 0;
         for (int j = 0; j < N; j++) {
             double dx = x[3 * j] - x[3 * i], dy = x[3 * j + 1] - x[3 * i + 1], dz = x[3 * j + 2] - x[3 * i + 2];
+            /* periodic topologies: the nearest image sets the scale (T^3: all axes, forces.cc:800-812; S^1xR^2: z, forces.cc:1320-1323) */
+            if (p->topology == 1) {
+                if (fabs(dx) > 0.5 * p->L) dx -= copysign(p->L, dx);
+                if (fabs(dy) > 0.5 * p->L) dy -= copysign(p->L, dy);
+            }
+            if (p->topology != 0 && fabs(dz) > 0.5 * p->L) dz -= copysign(p->L, dz);
             double r = sqrt(dx * dx + dy * dy + dz * dz);
             s += fabs(M[j] * oracle_force_softening_f64(r, soft[i] + soft[j])) * r;
         }

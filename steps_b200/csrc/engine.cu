@@ -170,6 +170,7 @@ constexpr int CTA_OVERHEAD_TILES = 2;
 
 struct Plan {
     int ib_size, n_ib, n_chunks, tiles_per_chunk, n_tiles, ctas, slots;
+    int sb = 1, n_sb = 0;  // action-reaction launch: i-blocks per superblock, number of superblocks
 };
 
 // Work units are (i-block, j-chunk) pairs of equal cost; the grid is dispatched in waves of `slots`
@@ -234,6 +235,11 @@ struct steps_b200_engine {
     void *d_gpart = nullptr, *d_fsym = nullptr;  // REAL of the build
     size_t gpart_bytes = 0;
     Plan last_sym_plan{};        // plan of the last action-reaction evaluation (the debug hook redoes its final reduction)
+    // superblock schedule of the action-reaction launch (built on the host for the plan in force, sym_schedule())
+    int sched_sb = 0, sched_rows = 0, sched_chunks = 0, sched_tpc = 0;  // what the tables below were built for
+    int2 *d_order = nullptr;             // per pass: its CTAs as (superblock within the pass, j-chunk), heaviest first
+    std::vector<int> pass_cta_off;       // [n_passes + 1] offsets into d_order
+    int2 *d_crange = nullptr;            // per local i-block: the j-chunks [lo, hi) that hold a partial sum for it
     // GLASS_MAKING mode: G = -1 and the diagnostics of step.cc:143-148, :270-303
     bool glass = false;
     double *d_glass_part = nullptr;  // [blocks][2*GLASS_NQ] per-block (sum, max) pairs
@@ -367,6 +373,9 @@ constexpr SymVariant SYM_VARIANTS[] = {
     {6, 128, 2, 1},  // 1: not unrolled
     {7, 128, 2, 2},  // 2: i-block 896 (a few spills outside the hot loop)
     {8, 128, 2, 2},  // 3: i-block 1024 (spills outside the hot loop)
+    {4, 128, 3, 2},  // 4: i-block 512, <= 168 registers, 3 CTAs/SM = 3 warps per scheduler (occupancy experiment of round 2)
+    {5, 128, 3, 2},  // 5: i-block 640, <= 168 registers, 3 CTAs/SM
+    {4, 128, 3, 4},  // 6: shape 4, visiting steps unrolled by 4
 };
 constexpr int N_SYM_VARIANTS = sizeof(SYM_VARIANTS) / sizeof(SYM_VARIANTS[0]);
 int sym_variant() {
@@ -387,6 +396,8 @@ bool sym_env_default() {
     return v == 1;
 }
 constexpr int SYM_TARGET_CHUNKS = 56;
+constexpr int SYM_SB_MAX = 8;     // default upper bound of i-blocks per superblock
+constexpr int SYM_SB_LIMIT = 64;  // what STEPS_B200_SYM_SB may ask for
 // FP32 shapes of the action-reaction kernel (pair_r3_sym_f32.cuh); STEPS_B200_SYM_F32_VARIANT=k
 constexpr SymVariant SYM32_VARIANTS[] = {
     {8, 128, 4, 2},   // 0: i-block 1024, <= 128 registers, 16 warps/SM
@@ -622,17 +633,25 @@ Plan sym_plan(const steps_b200_engine *e, int n_i) {
     p.n_ib = (n_i + p.ib_size - 1) / p.ib_size;
     p.n_tiles = e->n_tiles;
     p.slots = e->num_sms * sv.minb;
-    int target = SYM_TARGET_CHUNKS;
+    // A CTA works through one superblock (sb i-blocks, one j-side row per superblock and tile: pair_r3_sym.cuh) x one j-chunk.  About half
+    // of the (superblock, chunk) combinations carry work (each unordered block pair is evaluated once), and the grid should hold >= 16
+    // waves of working CTAs: sb = 8 whenever the job is large enough for that, fewer for small jobs; then as many chunks as it takes.
+    const long long needed = 32LL * p.slots;
+    const int max_chunks = std::max(1, p.n_tiles / MIN_TILES_PER_CHUNK);
+    p.sb = (int)std::max<long long>(1, std::min<long long>(SYM_SB_MAX, (long long)p.n_ib * max_chunks / needed));
+    if (const char *s = getenv("STEPS_B200_SYM_SB")) p.sb = std::max(1, std::min(SYM_SB_LIMIT, atoi(s)));
+    p.n_sb = (p.n_ib + p.sb - 1) / p.sb;
+    int target = (int)std::max<long long>(SYM_TARGET_CHUNKS, std::min<long long>(256, (needed + p.n_sb - 1) / p.n_sb));
     if (const char *s = getenv("STEPS_B200_SYM_CHUNKS")) {
         target = std::max(1, atoi(s));  // tuning knob
     } else {
         const size_t row_bytes = (size_t)3 * e->n_pad * e->real_bytes;
         const size_t rows = e->gpart_bytes ? e->gpart_bytes / row_bytes : std::max<size_t>(1, ((size_t)16 << 30) / row_bytes);
-        target = steps_b200_sym_chunk_target(p.n_tiles, p.n_ib, (long long)rows, p.slots);
+        target = std::max(target, steps_b200_sym_chunk_target(p.n_tiles, p.n_sb, (long long)rows, p.slots));
     }
     p.tiles_per_chunk = std::max(MIN_TILES_PER_CHUNK, (p.n_tiles + target - 1) / target);
     p.n_chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
-    p.ctas = p.n_ib * p.n_chunks;
+    p.ctas = p.n_sb * p.n_chunks;
     return p;
 }
 
@@ -784,7 +803,7 @@ template <typename T>
 int finish_pair_sym_t(steps_b200_engine *e, int id_min, int n_i, const Plan &pl) {
     reduce_kernel<T><<<(n_i + 255) / 256, 256, 0, e->stream>>>(static_cast<const T *>(e->d_fpart), pl.n_chunks, n_i, n_i, id_min,
                                                                 static_cast<const T *>(e->d_x), static_cast<T *>(e->d_F), e->tp,
-                                                                static_cast<const T *>(e->d_fsym), (size_t)e->n_pad);
+                                                                static_cast<const T *>(e->d_fsym), (size_t)e->n_pad, e->d_crange, pl.ib_size);
     e->launches++;
     CU_TRY(cudaGetLastError());
     return 0;
@@ -796,6 +815,73 @@ int finish_pair_sym(steps_b200_engine *e, int id_min, int n_i, const Plan &pl) {
 // Force evaluation of the engine's own rows by the action-reaction kernel: passes over groups of i-blocks (bounded
 // j-side partial buffer), each pass = pair kernel + j-side row reduction; then (multi-GPU) one all-reduce of the
 // j-side sums, then the usual chunk reduction, which also subtracts the j-side sum and adds the background term.
+// Host schedule of the action-reaction launch for plan pl with `rows` superblock rows per pass: for every pass the list of its CTAs
+// (superblock within the pass, j-chunk) that have work at all, heaviest first (cost = tiles the CTA evaluates, from the rules), ties in
+// chunk-major order so that concurrently running CTAs share their j-tiles in L2; and per i-block the chunks that will hold a partial sum.
+int sym_schedule(steps_b200_engine *e, const Plan &pl, int rows) {
+    if (e->d_order && e->sched_sb == pl.sb && e->sched_rows == rows && e->sched_chunks == pl.n_chunks && e->sched_tpc == pl.tiles_per_chunk)
+        return 0;
+    const int n_ib = (int)e->h_rules.size();
+    auto tiles_in = [](const SymRule &r, int c0, int c1) {
+        int n = std::max(0, std::min(r.diag_hi, c1) - std::max(r.diag_lo, c0));
+        for (int k = 0; k < r.n_sym; ++k) n += std::max(0, std::min(r.sym_hi[k], c1) - std::max(r.sym_lo[k], c0));
+        return n;
+    };
+    std::vector<int2> crange(n_ib);
+    for (int ib = 0; ib < n_ib; ++ib) {
+        int ha, hb;
+        sym_hull(e->h_rules[ib], 0, pl.n_tiles, ha, hb);
+        crange[ib] = ha < hb ? make_int2(ha / pl.tiles_per_chunk, (hb - 1) / pl.tiles_per_chunk + 1) : make_int2(0, 0);
+    }
+    struct Cta { int gs, jc, cost; };
+    std::vector<int2> order;
+    std::vector<int> off(1, 0);
+    std::vector<Cta> pass;
+    for (int s0 = 0; s0 < pl.n_sb; s0 += rows) {
+        const int ns = std::min(rows, pl.n_sb - s0);
+        pass.clear();
+        for (int gs = 0; gs < ns; ++gs) {
+            const int ib_lo = (s0 + gs) * pl.sb, ib_hi = std::min(ib_lo + pl.sb, n_ib);
+            int c_lo = pl.n_chunks, c_hi = 0;
+            for (int ib = ib_lo; ib < ib_hi; ++ib)
+                if (crange[ib].x < crange[ib].y) { c_lo = std::min(c_lo, crange[ib].x); c_hi = std::max(c_hi, crange[ib].y); }
+            for (int jc = c_lo; jc < c_hi; ++jc) {
+                const int c0 = jc * pl.tiles_per_chunk, c1 = std::min(c0 + pl.tiles_per_chunk, pl.n_tiles);
+                int cost = 0, hull = 0;
+                for (int ib = ib_lo; ib < ib_hi; ++ib) {
+                    cost += tiles_in(e->h_rules[ib], c0, c1);
+                    int ha, hb;
+                    sym_hull(e->h_rules[ib], c0, c1, ha, hb);
+                    hull += std::max(0, hb - ha);
+                }
+                if (hull > 0) pass.push_back({gs, jc, cost});
+            }
+        }
+        std::stable_sort(pass.begin(), pass.end(), [](const Cta &x, const Cta &y) {
+            if (x.cost != y.cost) return x.cost > y.cost;
+            if (x.jc != y.jc) return x.jc < y.jc;
+            return x.gs < y.gs;
+        });
+        for (const Cta &c : pass) order.push_back(make_int2(c.gs, c.jc));
+        off.push_back((int)order.size());
+    }
+    if (e->d_order) CU_TRY(cudaFree(e->d_order));
+    if (e->d_crange) CU_TRY(cudaFree(e->d_crange));
+    e->d_order = nullptr;
+    e->d_crange = nullptr;
+    CU_TRY(cudaMalloc(&e->d_order, std::max<size_t>(1, order.size()) * sizeof(int2)));
+    CU_TRY(cudaMalloc(&e->d_crange, std::max<size_t>(1, crange.size()) * sizeof(int2)));
+    CU_TRY(cudaMemcpyAsync(e->d_order, order.data(), order.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->d_crange, crange.data(), crange.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));  // the vectors die here
+    e->pass_cta_off.swap(off);
+    e->sched_sb = pl.sb;
+    e->sched_rows = rows;
+    e->sched_chunks = pl.n_chunks;
+    e->sched_tpc = pl.tiles_per_chunk;
+    return 0;
+}
+
 template <typename T>
 int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     using JRec = typename JRecOf<T>::type;
@@ -812,7 +898,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         size_t budget = std::min((size_t)16 << 30, free_b / 3);
         if (const char *s = getenv("STEPS_B200_SYM_GPART_MB")) budget = (size_t)atoll(s) << 20;
         size_t rows = std::max<size_t>(1, budget / row_bytes);
-        rows = std::min<size_t>(rows, (size_t)n_ib_call);
+        rows = std::min<size_t>(rows, (size_t)n_ib_call);  // (one row per superblock is what a pass needs: never more than this)
         // a smaller buffer only means more passes: halve until the allocation succeeds
         cudaError_t err = cudaErrorMemoryAllocation;
         while (rows >= 1) {
@@ -830,6 +916,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     const Plan pl = sym_plan(e, n_i);
     plan_out = pl;
     e->last_sym_plan = pl;
+    if (sym_schedule(e, pl, rows)) return 1;
     const size_t need = (size_t)pl.n_chunks * 3 * (size_t)n_i * sizeof(T);
     if (need > e->fpart_bytes) {
         if (e->d_fpart) CU_TRY(cudaFree(e->d_fpart));
@@ -852,42 +939,43 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     sa.rules = e->d_rules;
     sa.gpart = e->d_gpart;
     sa.n_pad = e->n_pad;
+    sa.a.n_ib = pl.n_ib;
+    sa.sb = pl.sb;
     const int nwarps = sv.threads / 32;
-    // staged tiles + tile bounds | warp bounds | visiting copy (x,y,z,m of each record twice) | 2 x per-warp accumulator slots | barriers
-    const size_t smem = F64 ? (size_t)F64_STAGES * (F64_TJ * sizeof(JRec64) + sizeof(TileInfo64)) + (size_t)nwarps * sizeof(WarpBounds64) +
-                                  (size_t)2 * nwarps * 3 * F64_TJ * sizeof(double) + (size_t)8 * F64_TJ * sizeof(double) +
-                                  2 * F64_STAGES * sizeof(uint64_t)
-                            : (size_t)F64_STAGES * (F64_TJ * sizeof(JRec32) + sizeof(TileInfo32)) + (size_t)nwarps * sizeof(WarpBounds32) +
-                                  (size_t)2 * F64_TJ * sizeof(float4) + (size_t)2 * nwarps * 3 * F64_TJ * sizeof(float) +
-                                  2 * F64_STAGES * sizeof(uint64_t);
+    // shared memory: the kernel's fixed buffers + the window of j-side accumulators (sym_window_tiles: what fits at the shape's occupancy)
+    const int base_smem = F64 ? sym_base_f64(nwarps, F64_STAGES, F64_TJ) : sym_base_f32(nwarps, F64_STAGES, F64_TJ);
+    const size_t smem = (size_t)base_smem + (size_t)sym_window_tiles(sv.minb, base_smem, (int)sizeof(T), F64_TJ) * 3 * F64_TJ * sizeof(T);
     (void)sizeof(JRec);
     CU_TRY(cudaEventRecord(e->ev[4], e->stream));
-    for (int b0 = 0; b0 < pl.n_ib; b0 += rows) {
-        const int nb = std::min(rows, pl.n_ib - b0);
-        sa.a.n_ib = nb;
+    for (int b0 = 0, pass = 0; b0 < pl.n_sb; b0 += rows, ++pass) {
+        const int nb = std::min(rows, pl.n_sb - b0);  // superblocks of this pass
+        const int n_cta = e->pass_cta_off[pass + 1] - e->pass_cta_off[pass];
         sa.b0 = b0;
+        sa.order = e->d_order + e->pass_cta_off[pass];
+        if (n_cta > 0) {
 #define LAUNCH_SYM(K)                                                                                                  \
     case K: {                                                                                                          \
         auto kern = force_r3_f64_sym_kernel<SYM_VARIANTS[K].R, SYM_VARIANTS[K].threads, F64_TJ, F64_STAGES, SYM_VARIANTS[K].minb, \
                                             SYM_VARIANTS[K].unroll>;                                                   \
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
-        kern<<<nb * pl.n_chunks, SYM_VARIANTS[K].threads, smem, e->stream>>>(sa);                                      \
+        kern<<<n_cta, SYM_VARIANTS[K].threads, smem, e->stream>>>(sa);                                      \
     } break;
 #define LAUNCH_SYM32(K)                                                                                                \
     case K: {                                                                                                          \
         auto kern = force_r3_f32_sym_kernel<SYM32_VARIANTS[K].R, SYM32_VARIANTS[K].threads, F64_TJ, F64_STAGES,        \
                                             SYM32_VARIANTS[K].minb, SYM32_VARIANTS[K].unroll>;                         \
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
-        kern<<<nb * pl.n_chunks, SYM32_VARIANTS[K].threads, smem, e->stream>>>(sa);                                    \
+        kern<<<n_cta, SYM32_VARIANTS[K].threads, smem, e->stream>>>(sa);                                    \
     } break;
         if (gen_sym_topology(e)) {
-            const size_t smem_gen = (size_t)GEN_STAGES * GEN_TJ * sizeof(JRec) + (size_t)2 * nwarps * 3 * GEN_TJ * sizeof(T) + 2 * GEN_STAGES * sizeof(uint64_t);
+            const int base_gen = sym_base_generic(nwarps, GEN_STAGES, (int)sizeof(JRec), (int)sizeof(T), GEN_TJ);
+            const size_t smem_gen = (size_t)base_gen + (size_t)sym_window_tiles(sv.minb, base_gen, (int)sizeof(T), GEN_TJ) * 3 * GEN_TJ * sizeof(T);
 #define LAUNCH_GEN_SYM_VT(V, TOPO, FASTV)                                                                                                \
     {                                                                                                                               \
         auto kern = force_generic_sym_kernel<T, TOPO, GEN_SYM_VARIANTS[V].R, GEN_SYM_VARIANTS[V].threads, GEN_TJ, GEN_STAGES,       \
                                              GEN_SYM_VARIANTS[V].minb, FASTV>;                                                      \
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gen));                             \
-        kern<<<nb * pl.n_chunks, GEN_SYM_VARIANTS[V].threads, smem_gen, e->stream>>>(sa, e->tp);                                    \
+        kern<<<n_cta, GEN_SYM_VARIANTS[V].threads, smem_gen, e->stream>>>(sa, e->tp);                                    \
     }
 #define LAUNCH_GEN_SYM_V(V)                                                   \
     case V:                                                                   \
@@ -909,7 +997,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         auto kern = force_s1r2nl_f64_sym_kernel<S1R2_SYM_VARIANTS[V].R, S1R2_SYM_VARIANTS[V].threads, F64_TJ, F64_STAGES,           \
                                                 S1R2_SYM_VARIANTS[V].minb, S1R2_SYM_VARIANTS[V].unroll, MM>;                        \
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                 \
-        kern<<<nb * pl.n_chunks, S1R2_SYM_VARIANTS[V].threads, smem, e->stream>>>(sa, k);                                           \
+        kern<<<n_cta, S1R2_SYM_VARIANTS[V].threads, smem, e->stream>>>(sa, k);                                           \
     }
 #define LAUNCH_S1R2_SYM_V(V)                                   \
     case V:                                                    \
@@ -921,7 +1009,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
 #undef LAUNCH_S1R2_SYM_V
 #undef LAUNCH_S1R2_SYM_VM
         } else if (F64) {
-            switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) LAUNCH_SYM(3) }
+            switch (sym_variant()) { LAUNCH_SYM(0) LAUNCH_SYM(1) LAUNCH_SYM(2) LAUNCH_SYM(3) LAUNCH_SYM(4) LAUNCH_SYM(5) LAUNCH_SYM(6) }
         } else {
             switch (sym32_variant()) { LAUNCH_SYM32(0) LAUNCH_SYM32(1) LAUNCH_SYM32(2) }
         }
@@ -929,8 +1017,9 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
 #undef LAUNCH_SYM32
         e->launches++;
         CU_TRY(cudaGetLastError());
-        reduce_sym_kernel<T><<<(e->n_pad + 255) / 256, 256, 0, e->stream>>>(static_cast<const T *>(e->d_gpart), e->d_rules, b0, nb, e->n_pad, TJ,
-                                                                             static_cast<T *>(e->d_fsym));
+        }
+        reduce_sym_kernel<T><<<(e->n_pad + 255) / 256, 256, 0, e->stream>>>(static_cast<const T *>(e->d_gpart), e->d_rules, b0, nb, pl.sb, pl.n_ib,
+                                                                             e->n_pad, TJ, static_cast<T *>(e->d_fsym));
         e->launches++;
         CU_TRY(cudaGetLastError());
     }
@@ -1105,7 +1194,7 @@ extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym, e->d_glass_part, e->d_glass};
+    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym, e->d_glass_part, e->d_glass, e->d_order, e->d_crange};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (e->h_errmax) cudaFreeHost(e->h_errmax);

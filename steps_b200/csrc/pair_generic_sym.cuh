@@ -142,54 +142,42 @@ __host__ __device__ __forceinline__ void pair_t3_fast_unit(const T3Fast &k, cons
     tz = fma(w, dz, -s2);
 }
 
+// shared memory of this kernel besides the window of j-side accumulators (pair_r3_sym.cuh: sym_window_tiles)
+__host__ __device__ constexpr int sym_base_generic(int nwarps, int stages, int jrec_bytes, int elem, int tj = 128) {
+    return stages * tj * jrec_bytes + 2 * nwarps * 3 * tj * elem + 2 * stages * 8;
+}
+
 template <typename T, int TOPO, int R, int THREADS, int TJ, int STAGES, int MINB, bool FAST>
 __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const SymLaunchArgs sa, const TopoParams tp) {
     using JRec = typename JRecOf<T>::type;
     constexpr int NWARPS = THREADS / 32;
     constexpr int IB = THREADS * R;
-    static_assert(THREADS >= TJ && TJ % 32 == 0 && IB % TJ == 0, "shape");
+    constexpr int WB = sym_window_tiles(MINB, sym_base_generic(NWARPS, STAGES, (int)sizeof(JRec), (int)sizeof(T), TJ), (int)sizeof(T), TJ);
+    static_assert(THREADS == TJ && TJ % 32 == 0 && IB % TJ == 0, "shape");
     const R3LaunchArgs &a = sa.a;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     JRec *tiles = reinterpret_cast<JRec *>(smem_raw);
     T *slots = reinterpret_cast<T *>(smem_raw + (size_t)STAGES * TJ * sizeof(JRec));  // [2][NWARPS][3][TJ]
-    uint64_t *full = reinterpret_cast<uint64_t *>(slots + 2 * NWARPS * 3 * TJ);
+    T *jacc = slots + 2 * NWARPS * 3 * TJ;  // [WB][3][TJ]: j-side sums of the current window (pair_r3_sym.cuh)
+    uint64_t *full = reinterpret_cast<uint64_t *>(jacc + (size_t)WB * 3 * TJ);
     uint64_t *empty = full + STAGES;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int jc = blockIdx.x / a.n_ib;
-    const int gb = blockIdx.x - jc * a.n_ib;
-    const int ib = sa.b0 + gb;
-    const SymRule *__restrict__ rule = sa.rules + ib;
-    int ta, tb;
-    {
-        const int c0 = jc * a.tiles_per_chunk;
-        const int c1 = min(c0 + a.tiles_per_chunk, a.n_tiles);
-        ta = 0x7fffffff;
-        tb = -1;
-        {
-            const int lo = max(rule->diag_lo, c0), hi = min(rule->diag_hi, c1);
-            if (lo < hi) { ta = min(ta, lo); tb = max(tb, hi); }
-        }
-        for (int q = 0; q < rule->n_sym; ++q) {
-            const int lo = max(rule->sym_lo[q], c0), hi = min(rule->sym_hi[q], c1);
-            if (lo < hi) { ta = min(ta, lo); tb = max(tb, hi); }
-        }
+    const int2 od = sa.order[blockIdx.x];
+    const int gs = od.x;  // superblock within the pass
+    const int jc = od.y;  // j-chunk
+    const int ib_lo = (sa.b0 + gs) * sa.sb;
+    const int ib_hi = min(ib_lo + sa.sb, a.n_ib);
+    const int c0 = jc * a.tiles_per_chunk;
+    const int c1 = min(c0 + a.tiles_per_chunk, a.n_tiles);
+    int TA = 0x7fffffff, TB = -1;  // tile range of the whole superblock inside this chunk
+    for (int ib = ib_lo; ib < ib_hi; ++ib) {
+        int ha, hb;
+        sym_hull(sa.rules[ib], c0, c1, ha, hb);
+        if (ha < hb) { TA = min(TA, ha); TB = max(TB, hb); }
     }
-    T *__restrict__ fp = static_cast<T *>(a.fpart) + (size_t)jc * 3 * a.fstride;
-    if (tb <= ta) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int il = ib * IB + r * THREADS + tid;
-            if (il < a.n_i) {
-                fp[il] = 0;
-                fp[a.fstride + il] = 0;
-                fp[2 * (size_t)a.fstride + il] = 0;
-            }
-        }
-        return;
-    }
-    const int t0 = ta, nt = tb - ta;
+    if (TB <= TA) return;  // (the host's order table holds no such CTA)
     const JRec *__restrict__ jrec = static_cast<const JRec *>(a.jrec);
 
     if (tid == 0) {
@@ -200,13 +188,37 @@ __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const 
         fence_mbar_init();
     }
     __syncthreads();
+    int nsym = 0;
+    int K0 = 0;  // tiles streamed so far by this CTA (pipeline stage / parity bookkeeping, pair_r3_sym.cuh)
+    static_assert(!FAST || TOPO == 1, "lean arithmetic exists for T^3 only");
+    T3Fast fk;
+    fk.L = (double)(T)tp.L;
+    fk.halfL = (double)((T)0.5 * (T)tp.L);
+    fk.inv_h = (double)((T)tp.dim0 / (T)tp.L);
+    fk.N = tp.dim0;
+    // (the engine launches the FAST instantiation only for IS_PERIODIC >= 2: the nearest-image-only sum has no table)
+
+    for (int w0 = TA; w0 < TB; w0 += WB) {
+    const int w1 = min(w0 + WB, TB);
+#pragma unroll 4
+    for (int q = 0; q < WB * 3; ++q) jacc[q * TJ + tid] = 0;
+    for (int ib = ib_lo; ib < ib_hi; ++ib) {
+    const SymRule *__restrict__ rule = sa.rules + ib;
+    int ha, hb;
+    sym_hull(*rule, c0, c1, ha, hb);
+    const int t0 = max(ha, w0), nt = min(hb, w1) - t0;
+    if (nt <= 0) continue;
+    const bool first = w0 <= ha;  // first window that reaches this block's tiles: the i-side sums start from zero
     if (tid == 0) {
         const int npre = nt < STAGES ? nt : STAGES;
         for (int t = 0; t < npre; ++t) {
-            mbar_arrive_expect_tx(&full[t], TJ * sizeof(JRec));
-            tma_load_1d(tiles + (size_t)t * TJ, jrec + (size_t)(t0 + t) * TJ, TJ * sizeof(JRec), &full[t]);
+            const int K = K0 + t;
+            sym_wait_stage_free<STAGES>(empty, K);
+            mbar_arrive_expect_tx(&full[K % STAGES], TJ * sizeof(JRec));
+            tma_load_1d(tiles + (size_t)(K % STAGES) * TJ, jrec + (size_t)(t0 + t) * TJ, TJ * sizeof(JRec), &full[K % STAGES]);
         }
     }
+    T *__restrict__ fp = static_cast<T *>(a.fpart) + (size_t)jc * 3 * a.fstride;
 
     T xi[R], yi[R], zi[R], si[R], mi[R], ax[R], ay[R], az[R];
 #pragma unroll
@@ -216,24 +228,23 @@ __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const 
         const JRec me = jrec[a.id_min + il];
         xi[r] = me.x; yi[r] = me.y; zi[r] = me.z; si[r] = me.s;
         mi[r] = il0 < a.n_i ? (T)me.m : (T)0;  // a clamped duplicate must not act on the j side
-        ax[r] = ay[r] = az[r] = 0;
+        if (first || il0 >= a.n_i) {
+            ax[r] = ay[r] = az[r] = 0;
+        } else {  // sums of the earlier windows of this chunk
+            ax[r] = fp[il0];
+            ay[r] = fp[a.fstride + il0];
+            az[r] = fp[2 * (size_t)a.fstride + il0];
+        }
     }
-    int nsym = 0;
-    static_assert(!FAST || TOPO == 1, "lean arithmetic exists for T^3 only");
-    T3Fast fk;
-    fk.L = (double)(T)tp.L;
-    fk.halfL = (double)((T)0.5 * (T)tp.L);
-    fk.inv_h = (double)((T)tp.dim0 / (T)tp.L);
-    fk.N = tp.dim0;
-    // (the engine launches the FAST instantiation only for IS_PERIODIC >= 2: the nearest-image-only sum has no table)
 
     for (int t = 0; t < nt; ++t) {
-        const int s = t % STAGES;
-        const uint32_t ph = (uint32_t)(t / STAGES) & 1u;
+        const int K = K0 + t;
+        const int s = K % STAGES;
+        const uint32_t ph = (uint32_t)(K / STAGES) & 1u;
         if (tid == 0 && t >= 1 && (t - 1 + STAGES) < nt) {
-            const int sp = (t - 1) % STAGES;
-            const uint32_t php = (uint32_t)((t - 1) / STAGES) & 1u;
-            mbar_wait(&empty[sp], php);
+            const int Kn = K - 1 + STAGES;
+            const int sp = Kn % STAGES;
+            sym_wait_stage_free<STAGES>(empty, Kn);
             mbar_arrive_expect_tx(&full[sp], TJ * sizeof(JRec));
             tma_load_1d(tiles + (size_t)sp * TJ, jrec + (size_t)(t0 + t - 1 + STAGES) * TJ, TJ * sizeof(JRec), &full[sp]);
         }
@@ -288,15 +299,16 @@ __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const 
                 slot[2 * TJ + g0 + lane] = vz;
             }
             __syncthreads();
-            if (tid < TJ) {
+            {
+                // the warps' sums in warp order onto the window's accumulator (blocks of the superblock arrive in block order)
                 const T *__restrict__ sb = slots + (size_t)(nsym & 1) * NWARPS * 3 * TJ;
-                T *__restrict__ gp = static_cast<T *>(sa.gpart) + (size_t)gb * 3 * sa.n_pad + (size_t)(t0 + t) * TJ + tid;
+                T *__restrict__ ja = jacc + (size_t)(t0 + t - w0) * 3 * TJ + tid;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     T v = 0;
 #pragma unroll
                     for (int w = 0; w < NWARPS; ++w) v += sb[((size_t)w * 3 + c) * TJ + tid];
-                    gp[(size_t)c * sa.n_pad] = v;
+                    ja[c * TJ] += v;
                 }
             }
             ++nsym;
@@ -304,6 +316,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const 
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
+    K0 += nt;
 
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -314,6 +327,16 @@ __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const 
             fp[2 * (size_t)a.fstride + il] = az[r];
         }
     }
+    }  // i-blocks of the superblock
+    // the window's j-side sums: one row segment per (superblock, tile); streamed (read once, by the row reduction)
+    {
+        T *__restrict__ gp = static_cast<T *>(sa.gpart) + (size_t)gs * 3 * sa.n_pad + (size_t)w0 * TJ + tid;
+        for (int tl = 0; tl < w1 - w0; ++tl) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) __stcs(gp + (size_t)c * sa.n_pad + (size_t)tl * TJ, jacc[(tl * 3 + c) * TJ + tid]);
+        }
+    }
+    }  // windows
 }
 
 }  // namespace steps

@@ -95,12 +95,19 @@ __device__ __forceinline__ void sym_tile_f32(const JRec32 *__restrict__ T, const
     }
 }
 
+// shared memory of the FP32 action-reaction kernel besides the window of j-side accumulators (pair_r3_sym.cuh: sym_window_tiles)
+__host__ __device__ constexpr int sym_base_f32(int nwarps, int stages, int tj = 128) {
+    return stages * (tj * 32 + 32) + nwarps * 48 + 2 * tj * 16 + 2 * nwarps * 3 * tj * 4 + 2 * stages * 8;
+}
+
 template <int R, int THREADS, int TJ, int STAGES, int MINB, int UNR>
 __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const SymLaunchArgs sa) {
     constexpr int NWARPS = THREADS / 32;
     constexpr int JB = 16;
     constexpr int IB = THREADS * R;
-    static_assert(THREADS >= TJ && TJ % 32 == 0 && IB % TJ == 0, "shape");
+    constexpr int WB = sym_window_tiles(MINB, sym_base_f32(NWARPS, STAGES, TJ), 4, TJ);
+    static_assert(sizeof(JRec32) == 32 && sizeof(TileInfo32) == 32 && sizeof(WarpBounds32) == 48, "sym_base_f32");
+    static_assert(THREADS == TJ && TJ % 32 == 0 && IB % TJ == 0, "shape");
     const R3LaunchArgs &a = sa.a;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     JRec32 *tiles = reinterpret_cast<JRec32 *>(smem_raw);
@@ -108,44 +115,26 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const S
     WarpBounds32 *wb_s = reinterpret_cast<WarpBounds32 *>(tinfo_s + STAGES);
     float4 *stage = reinterpret_cast<float4 *>(wb_s + NWARPS);                 // [TJ/32][64]
     float *slots = reinterpret_cast<float *>(stage + 2 * TJ);                   // [2][NWARPS][3][TJ]
-    uint64_t *full = reinterpret_cast<uint64_t *>(slots + 2 * NWARPS * 3 * TJ);
+    float *jacc = slots + 2 * NWARPS * 3 * TJ;                                  // [WB][3][TJ]: j-side sums of the current window (pair_r3_sym.cuh)
+    uint64_t *full = reinterpret_cast<uint64_t *>(jacc + (size_t)WB * 3 * TJ);
     uint64_t *empty = full + STAGES;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int jc = blockIdx.x / a.n_ib;
-    const int gb = blockIdx.x - jc * a.n_ib;
-    const int ib = sa.b0 + gb;
-    const SymRule *__restrict__ rule = sa.rules + ib;
-    int ta, tb;
-    {
-        const int c0 = jc * a.tiles_per_chunk;
-        const int c1 = min(c0 + a.tiles_per_chunk, a.n_tiles);
-        ta = 0x7fffffff;
-        tb = -1;
-        {
-            const int lo = max(rule->diag_lo, c0), hi = min(rule->diag_hi, c1);
-            if (lo < hi) { ta = min(ta, lo); tb = max(tb, hi); }
-        }
-        for (int k = 0; k < rule->n_sym; ++k) {
-            const int lo = max(rule->sym_lo[k], c0), hi = min(rule->sym_hi[k], c1);
-            if (lo < hi) { ta = min(ta, lo); tb = max(tb, hi); }
-        }
+    const int2 od = sa.order[blockIdx.x];
+    const int gs = od.x;  // superblock within the pass
+    const int jc = od.y;  // j-chunk
+    const int ib_lo = (sa.b0 + gs) * sa.sb;
+    const int ib_hi = min(ib_lo + sa.sb, a.n_ib);
+    const int c0 = jc * a.tiles_per_chunk;
+    const int c1 = min(c0 + a.tiles_per_chunk, a.n_tiles);
+    int TA = 0x7fffffff, TB = -1;  // tile range of the whole superblock inside this chunk
+    for (int ib = ib_lo; ib < ib_hi; ++ib) {
+        int ha, hb;
+        sym_hull(sa.rules[ib], c0, c1, ha, hb);
+        if (ha < hb) { TA = min(TA, ha); TB = max(TB, hb); }
     }
-    float *__restrict__ fp = static_cast<float *>(a.fpart) + (size_t)jc * 3 * a.fstride;
-    if (tb <= ta) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int il = ib * IB + r * THREADS + tid;
-            if (il < a.n_i) {
-                fp[il] = 0.f;
-                fp[a.fstride + il] = 0.f;
-                fp[2 * (size_t)a.fstride + il] = 0.f;
-            }
-        }
-        return;
-    }
-    const int t0 = ta, nt = tb - ta;
+    if (TB <= TA) return;  // (the host's order table holds no such CTA)
     const JRec32 *__restrict__ jrec = static_cast<const JRec32 *>(a.jrec);
     const TileInfo32 *__restrict__ tinfo = static_cast<const TileInfo32 *>(a.tinfo);
     constexpr uint32_t TILE_TX = TJ * sizeof(JRec32) + sizeof(TileInfo32);
@@ -158,14 +147,32 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const S
         fence_mbar_init();
     }
     __syncthreads();
+    const WarpBounds32 *__restrict__ wb = wb_s + warp;
+    int nsym = 0;
+    int K0 = 0;  // tiles streamed so far by this CTA (pipeline stage / parity bookkeeping, pair_r3_sym.cuh)
+
+    for (int w0 = TA; w0 < TB; w0 += WB) {
+    const int w1 = min(w0 + WB, TB);
+#pragma unroll 4
+    for (int k = 0; k < WB * 3; ++k) jacc[k * TJ + tid] = 0.f;
+    for (int ib = ib_lo; ib < ib_hi; ++ib) {
+    const SymRule *__restrict__ rule = sa.rules + ib;
+    int ha, hb;
+    sym_hull(*rule, c0, c1, ha, hb);
+    const int t0 = max(ha, w0), nt = min(hb, w1) - t0;
+    if (nt <= 0) continue;
+    const bool first = w0 <= ha;  // first window that reaches this block's tiles: the i-side sums start from zero
     if (tid == 0) {
         const int npre = nt < STAGES ? nt : STAGES;
         for (int t = 0; t < npre; ++t) {
-            mbar_arrive_expect_tx(&full[t], TILE_TX);
-            tma_load_1d(tiles + (size_t)t * TJ, jrec + (size_t)(t0 + t) * TJ, TJ * sizeof(JRec32), &full[t]);
-            tma_load_1d(tinfo_s + t, tinfo + (t0 + t), sizeof(TileInfo32), &full[t]);
+            const int K = K0 + t;
+            sym_wait_stage_free<STAGES>(empty, K);
+            mbar_arrive_expect_tx(&full[K % STAGES], TILE_TX);
+            tma_load_1d(tiles + (size_t)(K % STAGES) * TJ, jrec + (size_t)(t0 + t) * TJ, TJ * sizeof(JRec32), &full[K % STAGES]);
+            tma_load_1d(tinfo_s + (K % STAGES), tinfo + (t0 + t), sizeof(TileInfo32), &full[K % STAGES]);
         }
     }
+    float *__restrict__ fp = static_cast<float *>(a.fpart) + (size_t)jc * 3 * a.fstride;
 
     float xi[R], yi[R], zi[R], mi[R], ax[R], ay[R], az[R];
     {
@@ -177,7 +184,13 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const S
             const JRec32 me = jrec[a.id_min + il];
             xi[r] = me.x; yi[r] = me.y; zi[r] = me.z;
             mi[r] = il0 < a.n_i ? me.m : 0.f;  // a clamped duplicate must not act on the j side
-            ax[r] = ay[r] = az[r] = 0.f;
+            if (first || il0 >= a.n_i) {
+                ax[r] = ay[r] = az[r] = 0.f;
+            } else {  // sums of the earlier windows of this chunk
+                ax[r] = fp[il0];
+                ay[r] = fp[a.fstride + il0];
+                az[r] = fp[2 * (size_t)a.fstride + il0];
+            }
             lo[0] = fminf(lo[0], me.x); hi[0] = fmaxf(hi[0], me.x);
             lo[1] = fminf(lo[1], me.y); hi[1] = fmaxf(hi[1], me.y);
             lo[2] = fminf(lo[2], me.z); hi[2] = fmaxf(hi[2], me.z);
@@ -197,23 +210,22 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const S
             smx = fmaxf(smx, __shfl_xor_sync(0xffffffffu, smx, o));
         }
         if (lane == 0) {
-            WarpBounds32 &wb = wb_s[warp];
-            wb.lo[0] = lo[0]; wb.lo[1] = lo[1]; wb.lo[2] = lo[2];
-            wb.hi[0] = hi[0]; wb.hi[1] = hi[1]; wb.hi[2] = hi[2];
-            wb.rlo = rlo; wb.rhi = rhi; wb.smax = smx;
+            WarpBounds32 &wbw = wb_s[warp];
+            wbw.lo[0] = lo[0]; wbw.lo[1] = lo[1]; wbw.lo[2] = lo[2];
+            wbw.hi[0] = hi[0]; wbw.hi[1] = hi[1]; wbw.hi[2] = hi[2];
+            wbw.rlo = rlo; wbw.rhi = rhi; wbw.smax = smx;
         }
         __syncwarp();
     }
-    const WarpBounds32 *__restrict__ wb = wb_s + warp;
-    int nsym = 0;
 
     for (int t = 0; t < nt; ++t) {
-        const int s = t % STAGES;
-        const uint32_t ph = (uint32_t)(t / STAGES) & 1u;
+        const int K = K0 + t;
+        const int s = K % STAGES;
+        const uint32_t ph = (uint32_t)(K / STAGES) & 1u;
         if (tid == 0 && t >= 1 && (t - 1 + STAGES) < nt) {
-            const int sp = (t - 1) % STAGES;
-            const uint32_t php = (uint32_t)((t - 1) / STAGES) & 1u;
-            mbar_wait(&empty[sp], php);
+            const int Kn = K - 1 + STAGES;
+            const int sp = Kn % STAGES;
+            sym_wait_stage_free<STAGES>(empty, Kn);
             mbar_arrive_expect_tx(&full[sp], TILE_TX);
             tma_load_1d(tiles + (size_t)sp * TJ, jrec + (size_t)(t0 + t - 1 + STAGES) * TJ, TJ * sizeof(JRec32), &full[sp]);
             tma_load_1d(tinfo_s + sp, tinfo + (t0 + t - 1 + STAGES), sizeof(TileInfo32), &full[sp]);
@@ -276,7 +288,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const S
                 }
             } else {
                 float *__restrict__ slot = slots + ((size_t)(nsym & 1) * NWARPS + warp) * 3 * TJ;
-                if (tid < TJ) {
+                {
                     const float4 q4 = *reinterpret_cast<const float4 *>(&T[tid].x);
                     float4 *__restrict__ sq = stage + (tid >> 5) * 64 + (tid & 31);
                     sq[0] = q4;
@@ -288,15 +300,16 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const S
                 else
                     sym_tile_f32<R, TJ, THREADS, true, UNR>(T, stage, lane, tid, xi, yi, zi, mi, ax, ay, az, thr, slot, jrec, a.id_min, a.n_i, ib);
                 __syncthreads();
-                if (tid < TJ) {
+                {
+                    // the warps' sums in warp order onto the window's accumulator (blocks of the superblock arrive in block order)
                     const float *__restrict__ sb = slots + (size_t)(nsym & 1) * NWARPS * 3 * TJ;
-                    float *__restrict__ gp = static_cast<float *>(sa.gpart) + (size_t)gb * 3 * sa.n_pad + (size_t)(t0 + t) * TJ + tid;
+                    float *__restrict__ ja = jacc + (size_t)(t0 + t - w0) * 3 * TJ + tid;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         float v = 0.f;
 #pragma unroll
                         for (int w = 0; w < NWARPS; ++w) v += sb[((size_t)w * 3 + c) * TJ + tid];
-                        gp[(size_t)c * sa.n_pad] = v;
+                        ja[c * TJ] += v;
                     }
                 }
                 ++nsym;
@@ -305,6 +318,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const S
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
+    K0 += nt;
 
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -315,6 +329,16 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const S
             fp[2 * (size_t)a.fstride + il] = az[r];
         }
     }
+    }  // i-blocks of the superblock
+    // the window's j-side sums: one row segment per (superblock, tile); streamed (read once, by the row reduction)
+    {
+        float *__restrict__ gp = static_cast<float *>(sa.gpart) + (size_t)gs * 3 * sa.n_pad + (size_t)w0 * TJ + tid;
+        for (int tl = 0; tl < w1 - w0; ++tl) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) __stcs(gp + (size_t)c * sa.n_pad + (size_t)tl * TJ, jacc[(tl * 3 + c) * TJ + tid]);
+        }
+    }
+    }  // windows
 }
 
 }  // namespace steps

@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(THREADS, MINB) force_s1r2nl_f64_sym_kernel(con
     constexpr int NWARPS = THREADS / 32;
     constexpr int JB = 16;
     constexpr int IB = THREADS * R;
-    static_assert(THREADS >= TJ && TJ % 32 == 0 && IB % TJ == 0 && TJ % JB == 0, "shape");
+    constexpr int WB = sym_window_tiles(MINB, sym_base_f64(NWARPS, STAGES, TJ), 8, TJ);
+    static_assert(THREADS == TJ && TJ % 32 == 0 && IB % TJ == 0 && TJ % JB == 0, "shape");
     const R3LaunchArgs &a = sa.a;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     JRec64 *tiles = reinterpret_cast<JRec64 *>(smem_raw);
@@ -134,44 +135,26 @@ __global__ void __launch_bounds__(THREADS, MINB) force_s1r2nl_f64_sym_kernel(con
     WarpBounds64 *wb_s = reinterpret_cast<WarpBounds64 *>(tinfo_s + STAGES);
     double *slots = reinterpret_cast<double *>(wb_s + NWARPS);  // [2][NWARPS][3][TJ]
     double *soa = slots + 2 * NWARPS * 3 * TJ;                  // staged (x,y) / (z,m) copy of the current symmetric tile
-    uint64_t *full = reinterpret_cast<uint64_t *>(soa + 8 * TJ);
+    double *jacc = soa + 8 * TJ;                                // [WB][3][TJ]: j-side sums of the current window (pair_r3_sym.cuh)
+    uint64_t *full = reinterpret_cast<uint64_t *>(jacc + (size_t)WB * 3 * TJ);
     uint64_t *empty = full + STAGES;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int jc = blockIdx.x / a.n_ib;
-    const int gb = blockIdx.x - jc * a.n_ib;
-    const int ib = sa.b0 + gb;
-    const SymRule *__restrict__ rule = sa.rules + ib;
-    int ta, tb;
-    {
-        const int c0 = jc * a.tiles_per_chunk;
-        const int c1 = min(c0 + a.tiles_per_chunk, a.n_tiles);
-        ta = 0x7fffffff;
-        tb = -1;
-        {
-            const int lo = max(rule->diag_lo, c0), hi = min(rule->diag_hi, c1);
-            if (lo < hi) { ta = min(ta, lo); tb = max(tb, hi); }
-        }
-        for (int q = 0; q < rule->n_sym; ++q) {
-            const int lo = max(rule->sym_lo[q], c0), hi = min(rule->sym_hi[q], c1);
-            if (lo < hi) { ta = min(ta, lo); tb = max(tb, hi); }
-        }
+    const int2 od = sa.order[blockIdx.x];
+    const int gs = od.x;  // superblock within the pass
+    const int jc = od.y;  // j-chunk
+    const int ib_lo = (sa.b0 + gs) * sa.sb;
+    const int ib_hi = min(ib_lo + sa.sb, a.n_ib);
+    const int c0 = jc * a.tiles_per_chunk;
+    const int c1 = min(c0 + a.tiles_per_chunk, a.n_tiles);
+    int TA = 0x7fffffff, TB = -1;  // tile range of the whole superblock inside this chunk
+    for (int ib = ib_lo; ib < ib_hi; ++ib) {
+        int ha, hb;
+        sym_hull(sa.rules[ib], c0, c1, ha, hb);
+        if (ha < hb) { TA = min(TA, ha); TB = max(TB, hb); }
     }
-    double *__restrict__ fp = static_cast<double *>(a.fpart) + (size_t)jc * 3 * a.fstride;
-    if (tb <= ta) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int il = ib * IB + r * THREADS + tid;
-            if (il < a.n_i) {
-                fp[il] = 0.0;
-                fp[a.fstride + il] = 0.0;
-                fp[2 * (size_t)a.fstride + il] = 0.0;
-            }
-        }
-        return;
-    }
-    const int t0 = ta, nt = tb - ta;
+    if (TB <= TA) return;  // (the host's order table holds no such CTA)
     const JRec64 *__restrict__ jrec = static_cast<const JRec64 *>(a.jrec);
     const TileInfo64 *__restrict__ tinfo = static_cast<const TileInfo64 *>(a.tinfo);
     constexpr uint32_t TILE_TX = TJ * sizeof(JRec64) + sizeof(TileInfo64);
@@ -184,14 +167,42 @@ __global__ void __launch_bounds__(THREADS, MINB) force_s1r2nl_f64_sym_kernel(con
         fence_mbar_init();
     }
     __syncthreads();
+    const WarpBounds64 *__restrict__ wb = wb_s + warp;
+    S1R2SymRegs k;
+    k.L = kc.L;
+    k.LM1 = ((double)(M - 1)) * kc.L;  // (T)m * L as the reference forms it
+    k.LM = ((double)M) * kc.L;
+    asm volatile("mov.b64 %0, %0;" : "+d"(k.LM));  // as pair_s1r2.cuh: keep M*L in a vector register for the sign select
+    k.cut_bits = __double_as_longlong(kc.cut);
+    k.cutneg_bits = (unsigned long long)k.cut_bits | 0x8000000000000000ull;
+    const double L = k.L, LM1 = k.LM1, LM = k.LM;
+    const long long cut_bits = k.cut_bits;
+    const unsigned long long cutneg_bits = k.cutneg_bits;
+    int nsym = 0;
+    int K0 = 0;  // tiles streamed so far by this CTA (pipeline stage / parity bookkeeping, pair_r3_sym.cuh)
+
+    for (int w0 = TA; w0 < TB; w0 += WB) {
+    const int w1 = min(w0 + WB, TB);
+#pragma unroll 4
+    for (int q = 0; q < WB * 3; ++q) jacc[q * TJ + tid] = 0.0;
+    for (int ib = ib_lo; ib < ib_hi; ++ib) {
+    const SymRule *__restrict__ rule = sa.rules + ib;
+    int ha, hb;
+    sym_hull(*rule, c0, c1, ha, hb);
+    const int t0 = max(ha, w0), nt = min(hb, w1) - t0;
+    if (nt <= 0) continue;
+    const bool first = w0 <= ha;  // first window that reaches this block's tiles: the i-side sums start from zero
     if (tid == 0) {
         const int npre = nt < STAGES ? nt : STAGES;
         for (int t = 0; t < npre; ++t) {
-            mbar_arrive_expect_tx(&full[t], TILE_TX);
-            tma_load_1d(tiles + (size_t)t * TJ, jrec + (size_t)(t0 + t) * TJ, TJ * sizeof(JRec64), &full[t]);
-            tma_load_1d(tinfo_s + t, tinfo + (t0 + t), sizeof(TileInfo64), &full[t]);
+            const int K = K0 + t;
+            sym_wait_stage_free<STAGES>(empty, K);
+            mbar_arrive_expect_tx(&full[K % STAGES], TILE_TX);
+            tma_load_1d(tiles + (size_t)(K % STAGES) * TJ, jrec + (size_t)(t0 + t) * TJ, TJ * sizeof(JRec64), &full[K % STAGES]);
+            tma_load_1d(tinfo_s + (K % STAGES), tinfo + (t0 + t), sizeof(TileInfo64), &full[K % STAGES]);
         }
     }
+    double *__restrict__ fp = static_cast<double *>(a.fpart) + (size_t)jc * 3 * a.fstride;
 
     double xi[R], yi[R], zi[R], mi[R], ax[R], ay[R], az[R];
     {
@@ -204,7 +215,13 @@ __global__ void __launch_bounds__(THREADS, MINB) force_s1r2nl_f64_sym_kernel(con
             const JRec64 me = jrec[a.id_min + il];
             xi[r] = me.x; yi[r] = me.y; zi[r] = me.z;
             mi[r] = il0 < a.n_i ? me.m : 0.0;  // a clamped duplicate must not act on the j side
-            ax[r] = ay[r] = az[r] = 0.0;
+            if (first || il0 >= a.n_i) {
+                ax[r] = ay[r] = az[r] = 0.0;
+            } else {  // sums of the earlier windows of this chunk
+                ax[r] = fp[il0];
+                ay[r] = fp[a.fstride + il0];
+                az[r] = fp[2 * (size_t)a.fstride + il0];
+            }
             lo[0] = fmin(lo[0], me.x); hi[0] = fmax(hi[0], me.x);
             lo[1] = fmin(lo[1], me.y); hi[1] = fmax(hi[1], me.y);
             const double rr = sqrt(me.x * me.x + me.y * me.y);
@@ -223,33 +240,22 @@ __global__ void __launch_bounds__(THREADS, MINB) force_s1r2nl_f64_sym_kernel(con
             smx = fmax(smx, __shfl_xor_sync(0xffffffffu, smx, o));
         }
         if (lane == 0) {
-            WarpBounds64 &wb = wb_s[warp];
-            wb.lo[0] = lo[0]; wb.lo[1] = lo[1]; wb.lo[2] = 0.0;
-            wb.hi[0] = hi[0]; wb.hi[1] = hi[1]; wb.hi[2] = 0.0;
-            wb.rlo = rlo; wb.rhi = rhi; wb.smax = smx * 1.0000001; wb.pad = 0.0;
+            WarpBounds64 &wbw = wb_s[warp];
+            wbw.lo[0] = lo[0]; wbw.lo[1] = lo[1]; wbw.lo[2] = 0.0;
+            wbw.hi[0] = hi[0]; wbw.hi[1] = hi[1]; wbw.hi[2] = 0.0;
+            wbw.rlo = rlo; wbw.rhi = rhi; wbw.smax = smx * 1.0000001; wbw.pad = 0.0;
         }
         __syncwarp();
     }
-    const WarpBounds64 *__restrict__ wb = wb_s + warp;
-    S1R2SymRegs k;
-    k.L = kc.L;
-    k.LM1 = ((double)(M - 1)) * kc.L;  // (T)m * L as the reference forms it
-    k.LM = ((double)M) * kc.L;
-    asm volatile("mov.b64 %0, %0;" : "+d"(k.LM));  // as pair_s1r2.cuh: keep M*L in a vector register for the sign select
-    k.cut_bits = __double_as_longlong(kc.cut);
-    k.cutneg_bits = (unsigned long long)k.cut_bits | 0x8000000000000000ull;
-    const double L = k.L, LM1 = k.LM1, LM = k.LM;
-    const long long cut_bits = k.cut_bits;
-    const unsigned long long cutneg_bits = k.cutneg_bits;
-    int nsym = 0;
 
     for (int t = 0; t < nt; ++t) {
-        const int s = t % STAGES;
-        const uint32_t ph = (uint32_t)(t / STAGES) & 1u;
+        const int K = K0 + t;
+        const int s = K % STAGES;
+        const uint32_t ph = (uint32_t)(K / STAGES) & 1u;
         if (tid == 0 && t >= 1 && (t - 1 + STAGES) < nt) {
-            const int sp = (t - 1) % STAGES;
-            const uint32_t php = (uint32_t)((t - 1) / STAGES) & 1u;
-            mbar_wait(&empty[sp], php);
+            const int Kn = K - 1 + STAGES;
+            const int sp = Kn % STAGES;
+            sym_wait_stage_free<STAGES>(empty, Kn);
             mbar_arrive_expect_tx(&full[sp], TILE_TX);
             tma_load_1d(tiles + (size_t)sp * TJ, jrec + (size_t)(t0 + t - 1 + STAGES) * TJ, TJ * sizeof(JRec64), &full[sp]);
             tma_load_1d(tinfo_s + sp, tinfo + (t0 + t - 1 + STAGES), sizeof(TileInfo64), &full[sp]);
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_s1r2nl_f64_sym_kernel(con
             } else {
                 // ---- symmetric tile: systolic visit of 32 records per group ----
                 double *__restrict__ slot = slots + ((size_t)(nsym & 1) * NWARPS + warp) * 3 * TJ;
-                if (tid < TJ) {
+                {
                     const double2 xy = *reinterpret_cast<const double2 *>(&T[tid].x);
                     const double2 zm = *reinterpret_cast<const double2 *>(&T[tid].z);
                     double2 *__restrict__ sxy = reinterpret_cast<double2 *>(soa) + (tid >> 5) * 64 + (tid & 31);
@@ -334,15 +340,16 @@ __global__ void __launch_bounds__(THREADS, MINB) force_s1r2nl_f64_sym_kernel(con
                 else
                     sym_tile_s1r2<R, TJ, THREADS, true, UNR, M>(T, soa, lane, tid, xi, yi, zi, mi, ax, ay, az, thr, slot, jrec, a.id_min, a.n_i, ib, k);
                 __syncthreads();
-                if (tid < TJ) {
+                {
+                    // the warps' sums in warp order onto the window's accumulator (blocks of the superblock arrive in block order)
                     const double *__restrict__ sb = slots + (size_t)(nsym & 1) * NWARPS * 3 * TJ;
-                    double *__restrict__ gp = static_cast<double *>(sa.gpart) + (size_t)gb * 3 * sa.n_pad + (size_t)(t0 + t) * TJ + tid;
+                    double *__restrict__ ja = jacc + (size_t)(t0 + t - w0) * 3 * TJ + tid;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         double v = 0.0;
 #pragma unroll
                         for (int w = 0; w < NWARPS; ++w) v += sb[((size_t)w * 3 + c) * TJ + tid];
-                        gp[(size_t)c * sa.n_pad] = v;
+                        ja[c * TJ] += v;
                     }
                 }
                 ++nsym;
@@ -351,6 +358,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_s1r2nl_f64_sym_kernel(con
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
+    K0 += nt;
 
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -361,6 +369,16 @@ __global__ void __launch_bounds__(THREADS, MINB) force_s1r2nl_f64_sym_kernel(con
             fp[2 * (size_t)a.fstride + il] = az[r];
         }
     }
+    }  // i-blocks of the superblock
+    // the window's j-side sums: one row segment per (superblock, tile); streamed (read once, by the row reduction)
+    {
+        double *__restrict__ gp = static_cast<double *>(sa.gpart) + (size_t)gs * 3 * sa.n_pad + (size_t)w0 * TJ + tid;
+        for (int tl = 0; tl < w1 - w0; ++tl) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) __stcs(gp + (size_t)c * sa.n_pad + (size_t)tl * TJ, jacc[(tl * 3 + c) * TJ + tid]);
+        }
+    }
+    }  // windows
 }
 
 }  // namespace steps

@@ -305,7 +305,23 @@ def make_roofline(args, c, eng, world, pk_ms, ms_step, pairs_per_launch, peak_su
     instr = None
     if topo == 0:
         instr = ((10 if symmetric else 15) if rb == 8 else (9.5 if symmetric else 14))
-    return dict(common, bound="fp64_pipe" if rb == 8 else "fp32_pipe",
+    elif topo == 3 and rb == 8 and 2 <= g.IS_PERIODIC <= 4:
+        # SASS of the far loops: 2M image slots x 10 + 13 FP64 instructions per unordered pair (action-reaction),
+        # (2M+1) x 9 + 5 per directed pair (one-sided); M = IS_PERIODIC + 1
+        M = g.IS_PERIODIC + 1
+        instr = (2 * M * 10 + 13) / 2.0 if symmetric else (2 * M + 1) * 9 + 5
+    lanes = 64 if rb == 8 else 128
+    util = None
+    if instr is not None:
+        # what the pipe physically does: FP instructions per directed interaction x interactions/s / (lanes x SMs x clock)
+        util = instr * pairs_per_launch / (pk_ms * 1e-3) / (lanes * 148 * eng_clock_hz(peak_burst, rb))
+    note = None
+    if ev > 1:
+        note = ("frac follows SURVEY.md 8(d): 20 flop per IMAGE evaluation, counted per directed pair and image slot as the reference evaluates them.  "
+                "The kernel shares dx, dy, the masses and the accumulation across the image slots of a pair and (action-reaction) evaluates every "
+                "slot once for both particles, so it spends far fewer than 20 FP64 instructions per counted evaluation and frac can exceed 1; "
+                "fp_pipe_utilisation_model is the physical occupancy of the pipe")
+    return dict(common, note=note, fp_pipe_utilisation_model=util, bound="fp64_pipe" if rb == 8 else "fp32_pipe",
                 fp64_instr_per_interaction=instr if rb == 8 else None, fp32_instr_per_interaction=None if rb == 8 else instr,
                 achieved=achieved_tf, peak=peak_sust, unit="TFLOP/s", frac=achieved_tf / peak_sust, peak_burst=peak_burst,
                 frac_of_burst=achieved_tf / peak_burst, frac_of_nominal=achieved_tf / (37.2 if rb == 8 else 74.5),
@@ -372,7 +388,7 @@ def parity_block(c, eng, world, rank, dist, dev, fn_pack):
             "note": "forces held by the engines after the last timed step (rows gathered from the owning ranks) vs the reference's CPU forces() on the same positions"}
 
 
-def reference_cuda_leg(c, rows=16384):
+def reference_cuda_leg(c, target_s=6.0):
     """the kernel to beat: the reference's OWN CUDA path (forces_cuda.cu compiled unmodified for sm_100a by
     `make -C oracle refcuda`) timed on this GPU on a bounded row range of the same workload, through its own host-buffer call."""
     import numpy as np
@@ -388,9 +404,14 @@ def reference_cuda_leg(c, rows=16384):
     r.set_n_gpu(1)
     if g.topology != 0:
         r.build_tables()
-    rows = min(rows, g.N)
-    lo = (g.N - rows) // 2
-    r.forces(c.x, lo, min(lo + 255, lo + rows - 1), 0)  # context, first allocation
+    lo = g.N // 4
+    r.forces(c.x, lo, min(lo + 255, g.N - 1), 0)  # context, first allocation
+    # size the timed call for about target_s seconds (its fixed cost -- allocation, H2D of x, M, SOFT_LENGTH -- is part of the call)
+    probe = min(4096, g.N - lo)
+    t0 = time.perf_counter()
+    r.forces(c.x, lo, lo + probe - 1, 0)
+    tp = time.perf_counter() - t0
+    rows = int(max(probe, min(g.N - lo, probe * target_s / max(tp, 1e-6))))
     t0 = time.perf_counter()
     r.forces(c.x, lo, lo + rows - 1, 0)
     t = time.perf_counter() - t0

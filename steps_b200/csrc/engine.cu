@@ -221,6 +221,7 @@ struct steps_b200_engine {
     double *d_errmax = nullptr, *h_errmax = nullptr;
     size_t fpart_bytes = 0;
     size_t table_bytes = 0, radial_bytes = 0;
+    void *d_table_zwin = nullptr;  // T^3: aligned row copies of the Ewald table (t3_lookup.cuh), rebuilt whenever the table is uploaded
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // force begin/end, step begin/end, pair kernel begin/end
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // caller-placed (bench)
     long long launches = 0;
@@ -306,6 +307,7 @@ void fill_topo(steps_b200_engine *e) {
     if (p.topology == STEPS_TOPO_T3) t.bg_mode = 0;  // no background term in T^3 (forces_cuda.cu:567-645)
     t.table = e->d_table;
     t.radial = e->d_radial;
+    t.table_zwin = e->d_table_zwin;
 }
 
 // Tables are HOST pointers owned by the caller.  A resident engine uploads them once (create); the stateless
@@ -319,11 +321,24 @@ int upload_tables(steps_b200_engine *e) {
         const size_t bytes = ne * e->real_bytes;
         if (bytes != e->table_bytes) {
             if (e->d_table) CU_TRY(cudaFree(e->d_table));
+            if (e->d_table_zwin) CU_TRY(cudaFree(e->d_table_zwin));
             e->d_table = nullptr;
+            e->d_table_zwin = nullptr;
             CU_TRY(cudaMalloc(&e->d_table, bytes));
             e->table_bytes = bytes;
         }
         CU_TRY(cudaMemcpyAsync(e->d_table, p.ewald_table, bytes, cudaMemcpyHostToDevice, e->stream));
+        if (p.topology == STEPS_TOPO_T3) {
+            const int N = p.table_dim0;
+            const size_t elems = e->real_bytes == 8 ? t3_aligned_elems<double>(N) : t3_aligned_elems<float>(N);
+            if (!e->d_table_zwin) CU_TRY(cudaMalloc(&e->d_table_zwin, elems * e->real_bytes));
+            const int work = N * N * (16 / e->real_bytes);  // one thread per (copy, row)
+            if (e->real_bytes == 8)
+                t3_aligned_kernel<double><<<(work + 127) / 128, 128, 0, e->stream>>>((const double *)e->d_table, N, (double *)e->d_table_zwin);
+            else
+                t3_aligned_kernel<float><<<(work + 127) / 128, 128, 0, e->stream>>>((const float *)e->d_table, N, (float *)e->d_table_zwin);
+            CU_TRY(cudaGetLastError());
+        }
     }
     if (p.radial_table && p.radial_table_size > 0) {
         const size_t bytes = (size_t)p.radial_table_size * e->real_bytes;
@@ -1194,7 +1209,7 @@ extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym, e->d_glass_part, e->d_glass, e->d_order, e->d_crange};
+    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym, e->d_glass_part, e->d_glass, e->d_order, e->d_crange, e->d_table_zwin};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (e->h_errmax) cudaFreeHost(e->h_errmax);
@@ -1383,6 +1398,9 @@ extern "C" int steps_b200_engine_init_errmax(steps_b200_engine *e, double a, dou
     const KdkScalars k = kdk_scalars(e, 0.0, a, hubble);
     int rc = e->real_bytes == 8 ? errmax_launch<double>(e, k, 0, 1) : errmax_launch<float>(e, k, 0, 1);
     if (rc) return rc;
+    // the kernel wrapped the positions of this engine's OWN rows into the box (step.cc:41-70 wraps all N): bring every replica
+    // up to date, so that a force evaluation or a download before the next step sees the same positions on every rank
+    if (e->nranks > 1 && e->comm && e->p.topology != STEPS_TOPO_R3 && (rc = gather_positions(e))) return rc;
     return reduce_errmax(e, errmax_out);
 }
 
@@ -1572,9 +1590,10 @@ extern "C" int steps_b200_t3_ewald_table_f64(int ngrid, double L, double alpha, 
     if (device < 0 || device >= ndev) return fail("bad device ordinal");
     DeviceGuard dg_;
     CU_TRY(cudaSetDevice(device));
-    std::vector<EwaldIdx> re, rc;
-    build_ewald_space(rel_cut + 1.0, re);  // main.cc:467-468
-    build_ewald_space(rec_cut + 2.0, rc);
+    T3EwaldParams p{ngrid, L, alpha, rel_cut, rec_cut, 0, 0};
+    std::vector<LatticeShift> re;
+    std::vector<RecipMode> rc;
+    t3_ewald_prepare(p, re, rc);
     std::vector<int> pts;
     for (int i = ngrid / 2; i < ngrid; ++i)
         for (int j = ngrid / 2; j <= i; ++j)
@@ -1585,9 +1604,9 @@ extern "C" int steps_b200_t3_ewald_table_f64(int ngrid, double L, double alpha, 
             }
     const int n_points = (int)(pts.size() / 3);
     const size_t tab_bytes = (size_t)ngrid * ngrid * ngrid * 3 * sizeof(double);
-    T3EwaldParams p{ngrid, L, alpha, rel_cut, rec_cut, (int)re.size(), (int)rc.size()};
     int *d_pts = nullptr;
-    EwaldIdx *d_re = nullptr, *d_rc = nullptr;
+    LatticeShift *d_re = nullptr;
+    RecipMode *d_rc = nullptr;
     double *d_tab = nullptr;
     auto cleanup = [&]() {
         if (d_pts) cudaFree(d_pts);
@@ -1604,12 +1623,12 @@ extern "C" int steps_b200_t3_ewald_table_f64(int ngrid, double L, double alpha, 
         }                                                                                                    \
     } while (0)
     T_TRY(cudaMalloc(&d_pts, pts.size() * sizeof(int)));
-    T_TRY(cudaMalloc(&d_re, re.size() * sizeof(EwaldIdx)));
-    T_TRY(cudaMalloc(&d_rc, rc.size() * sizeof(EwaldIdx)));
+    T_TRY(cudaMalloc(&d_re, std::max<size_t>(1, re.size()) * sizeof(LatticeShift)));
+    T_TRY(cudaMalloc(&d_rc, std::max<size_t>(1, rc.size()) * sizeof(RecipMode)));
     T_TRY(cudaMalloc(&d_tab, tab_bytes));
     T_TRY(cudaMemcpy(d_pts, pts.data(), pts.size() * sizeof(int), cudaMemcpyHostToDevice));
-    T_TRY(cudaMemcpy(d_re, re.data(), re.size() * sizeof(EwaldIdx), cudaMemcpyHostToDevice));
-    T_TRY(cudaMemcpy(d_rc, rc.data(), rc.size() * sizeof(EwaldIdx), cudaMemcpyHostToDevice));
+    T_TRY(cudaMemcpy(d_re, re.data(), re.size() * sizeof(LatticeShift), cudaMemcpyHostToDevice));
+    T_TRY(cudaMemcpy(d_rc, rc.data(), rc.size() * sizeof(RecipMode), cudaMemcpyHostToDevice));
     T_TRY(cudaMemset(d_tab, 0, tab_bytes));
     t3_ewald_table_kernel<<<(n_points + 63) / 64, 64>>>(d_pts, n_points, p, d_re, d_rc, d_tab);
     T_TRY(cudaGetLastError());
@@ -1687,13 +1706,27 @@ namespace {
 constexpr int MAX_DEV = 16;
 steps_b200_engine *g_cached[2][MAX_DEV] = {};
 
+// what a cached engine's buffers AND its launch decisions (partition, action-reaction rules, tuned-kernel choice) depend on
 bool same_shape(const steps_b200_params &a, const steps_b200_params &b) {
     return a.topology == b.topology && a.n == b.n && a.table_dim0 == b.table_dim0 && a.table_dim1 == b.table_dim1 &&
-           a.radial_table_size == b.radial_table_size;
+           a.radial_table_size == b.radial_table_size && a.is_periodic == b.is_periodic && a.cosmology == b.cosmology &&
+           a.comoving == b.comoving;
 }
 
 // One engine per device, cached between calls; the i-range is split over the devices (every GPU holds the full
 // j replica, as forces_cuda.cu:933-951 does) and all devices run concurrently, driven from this one host thread.
+int group_refresh_params(steps_b200_group *g, const steps_b200_params *p);  // defined with the group, below
+struct CachedGroup {
+    steps_b200_group *g = nullptr;
+    steps_b200_params p{};
+    int n_gpu = 0, first_device = 0;
+};
+CachedGroup g_cached_group[2];
+bool multi_group_enabled() {
+    static const bool off = getenv("STEPS_B200_MULTI_ONESIDED") != nullptr;  // development switch: the i-range split of round 1
+    return !off;
+}
+
 int forces_stateless(const steps_b200_params *p, int real_bytes, const void *x, const void *M, const void *soft, void *F, int id_min,
                      int id_max, int n_gpu, int first_device) {
     if (check_params(p)) return 1;
@@ -1713,6 +1746,27 @@ int forces_stateless(const steps_b200_params *p, int real_bytes, const void *x, 
     const int n_i = id_max - id_min + 1;
     if (n_gpu > n_i) n_gpu = n_i;
     const int pi = real_bytes == 8 ? 0 : 1;
+    if (n_gpu > 1 && id_min == 0 && id_max == p->n - 1 && multi_group_enabled()) {
+        // A whole-range call over several GPUs (what forces_cuda(x, F, n_GPU, ...) is in a single-rank run): the resident group does
+        // it -- rows dealt out in i-blocks, the action-reaction kernel on every device, NCCL all-reduce of the j-side sums over
+        // NVLink -- instead of n_gpu independent one-sided sub-range launches.  The group is cached like the engines below.
+        CachedGroup &cg = g_cached_group[pi];
+        if (cg.g && (!same_shape(cg.p, *p) || cg.n_gpu != n_gpu || cg.first_device != first_device)) {
+            steps_b200_group_destroy(cg.g);
+            cg.g = nullptr;
+        }
+        if (!cg.g) {
+            if (steps_b200_group_create(&cg.g, p, real_bytes, n_gpu, first_device)) return 1;
+            cg.n_gpu = n_gpu;
+            cg.first_device = first_device;
+        } else {
+            if (group_refresh_params(cg.g, p)) return 1;
+        }
+        cg.p = *p;
+        if (steps_b200_group_upload(cg.g, x, nullptr, M, soft, nullptr)) return 1;
+        if (steps_b200_group_forces(cg.g)) return 1;
+        return steps_b200_group_download(cg.g, nullptr, nullptr, F);
+    }
     int lo[MAX_DEV], hi[MAX_DEV];
     DeviceGuard dg_;  // the caller's current device is restored on every return path
     for (int d = 0; d < n_gpu; ++d) {
@@ -1774,6 +1828,11 @@ extern "C" void steps_b200_release_cached(void) {
                 steps_b200_engine_destroy(e);
                 e = nullptr;
             }
+    for (auto &cg : g_cached_group)
+        if (cg.g) {
+            steps_b200_group_destroy(cg.g);
+            cg.g = nullptr;
+        }
 }
 
 // ------------------------------------------------------------------------------------------------ in-process multi-GPU group
@@ -1790,6 +1849,18 @@ struct steps_b200_group {
 };
 
 namespace {
+// a cached group meets the next stateless call: same shape, possibly new scalars and new table contents (re-uploaded like the
+// cached engines do, forces_stateless)
+int group_refresh_params(steps_b200_group *g, const steps_b200_params *p) {
+    for (auto *e : g->eng) {
+        e->p = *p;
+        DeviceGuard dg_;
+        CU_TRY(cudaSetDevice(e->device));
+        if (upload_tables(e)) return 1;
+    }
+    return 0;
+}
+
 // run fn(d) for every engine on its own thread; first error message wins
 template <typename Fn>
 int group_parallel(steps_b200_group *g, Fn fn) {

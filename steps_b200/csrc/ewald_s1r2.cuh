@@ -49,58 +49,69 @@ __host__ __device__ inline double s1r2_wrap(double dz, double Lz) {
     return dz;
 }
 
-// (D_rho, D_z) of one table cell (ewald_space.cc:754-798 with dx = rho, dy = 0)
-__host__ __device__ inline void s1r2_ewald_cell(int ir, int iz, const S1R2EwaldParams &p, double &Drho, double &Dz) {
-    const double pi = 3.14159265358979323846;
-    const double sqrtpi = 1.7724538509055160272981674833411;
-    const double drho = p.rho_max / (double)(p.nrho - 1 > 1 ? p.nrho - 1 : 1);
-    const double dzc = p.Lz / (double)p.nz;
-    const double rho = (double)ir * drho;
-    const double z = ((double)iz + 0.5) * dzc - 0.5 * p.Lz;
-    const double Lz = p.Lz, alpha = p.alpha;
-    const double dz = s1r2_wrap(z, Lz);
-    const double rho2 = rho * rho;
-    // real space
-    double Fxr = 0.0, Fzr = 0.0;
+// The periodic force on a unit mass at (rho, z) from a unit line of images along z, in three parts with their own loops, then the
+// Newtonian force of the nearest image is taken away (ewald_space.cc:618-798 with dx = rho, dy = 0).  Each part keeps the
+// reference's term order; the parts are separate functions so that the table builder reads as the formula in the header.
+struct SlabForce {
+    double radial, axial;
+};
+
+// screened Newtonian pull of the images n = -nmax .. nmax
+__host__ __device__ inline SlabForce s1r2_image_part(double rho, double dz, const S1R2EwaldParams &p) {
+    const double two_over_sqrtpi = 2.0 / 1.7724538509055160272981674833411;
+    SlabForce f{0.0, 0.0};
     for (int n = -p.nmax; n <= p.nmax; ++n) {
-        const double dzn = dz + (double)n * Lz;
-        const double r2 = rho2 + dzn * dzn;
-        if (r2 < 1e-18) continue;
-        const double r = sqrt(r2);
-        const double invr3 = 1.0 / (r2 * r);
-        const double ar = alpha * r;
-        const double coeff = (erfc(ar) + (2.0 / sqrtpi) * ar * exp(-ar * ar)) * invr3;
-        Fxr -= rho * coeff;
-        Fzr -= dzn * coeff;
+        const double zn = dz + (double)n * p.Lz;
+        const double d2 = rho * rho + zn * zn;
+        if (d2 < 1e-18) continue;
+        const double d = sqrt(d2);
+        const double ad = p.alpha * d;
+        const double screened = (erfc(ad) + two_over_sqrtpi * ad * exp(-ad * ad)) * (1.0 / (d2 * d));
+        f.radial -= rho * screened;
+        f.axial -= zn * screened;
     }
-    // k space
-    double Frk = 0.0, Fzk = 0.0;
-    const double invL = 1.0 / Lz;
+    return f;
+}
+
+// the modes m = 1 .. mmax of the singly periodic kernel and, off the axis, the zero mode
+__host__ __device__ inline SlabForce s1r2_mode_part(double rho, double dz, const S1R2EwaldParams &p) {
+    const double two_pi = 2.0 * 3.14159265358979323846;
+    const double per_length = 1.0 / p.Lz;
+    const double weight = 2.0 * per_length;
+    SlabForce f{0.0, 0.0};
     for (int m = 1; m <= p.mmax; ++m) {
-        const double km = (2.0 * pi * m) * invL;
-        const double tp = s1r2_exp_erfc(km, rho, alpha, true);
-        const double tm = s1r2_exp_erfc(km, rho, alpha, false);
-        const double B = tp + tm;
-        const double dBdrho = km * (tp - tm);
-        Frk += (2.0 * invL) * cos(km * dz) * dBdrho;
-        Fzk -= (2.0 * invL) * km * sin(km * dz) * B;
+        const double k = (two_pi * m) * per_length;
+        const double grow = s1r2_exp_erfc(k, rho, p.alpha, true);
+        const double decay = s1r2_exp_erfc(k, rho, p.alpha, false);
+        f.radial += weight * cos(k * dz) * (k * (grow - decay));
+        f.axial -= weight * k * sin(k * dz) * (grow + decay);
     }
-    if (rho > 1e-12) Frk += -(2.0 * invL / rho) * (1.0 - exp(-alpha * alpha * rho2));
-    const double Fxk = (rho > 0) ? (Frk * rho / rho) : 0.0;
-    const double Frho_periodic = Fxr + Fxk;
-    const double Fz_periodic = Fzr + Fzk;
-    // nearest-image Newton
-    const double dzw = s1r2_wrap(z, Lz);
-    const double r2 = rho * rho + dzw * dzw;
-    double Frho_newt = 0.0, Fz_newt = 0.0;
-    if (r2 > 0.0) {
-        const double r = sqrt(r2);
-        const double invr3 = 1.0 / (r * r * r);
-        Frho_newt = -rho * invr3;
-        Fz_newt = -dzw * invr3;
-    }
-    Drho = Frho_periodic - Frho_newt;
-    Dz = Fz_periodic - Fz_newt;
+    if (rho > 1e-12) f.radial += -(weight / rho) * (1.0 - exp(-p.alpha * p.alpha * (rho * rho)));
+    // (the reference projects the radial part on x with dx / rho = rho / rho: exactly 1 off the axis, nothing on it)
+    if (!(rho > 0)) f.radial = 0.0;
+    else f.radial = f.radial * rho / rho;
+    return f;
+}
+
+// plain Newtonian pull of the nearest image
+__host__ __device__ inline SlabForce s1r2_nearest_part(double rho, double dz) {
+    const double d2 = rho * rho + dz * dz;
+    if (!(d2 > 0.0)) return SlabForce{0.0, 0.0};
+    const double d = sqrt(d2);
+    const double inv3 = 1.0 / (d * d * d);
+    return SlabForce{-rho * inv3, -dz * inv3};
+}
+
+// (D_rho, D_z) of table cell (ir, iz): nodes in rho, cell centres in z
+__host__ __device__ inline void s1r2_ewald_cell(int ir, int iz, const S1R2EwaldParams &p, double &Drho, double &Dz) {
+    const double node = p.rho_max / (double)(p.nrho - 1 > 1 ? p.nrho - 1 : 1);
+    const double rho = (double)ir * node;
+    const double dz = s1r2_wrap(((double)iz + 0.5) * (p.Lz / (double)p.nz) - 0.5 * p.Lz, p.Lz);
+    const SlabForce images = s1r2_image_part(rho, dz, p);
+    const SlabForce modes = s1r2_mode_part(rho, dz, p);
+    const SlabForce nearest = s1r2_nearest_part(rho, dz);
+    Drho = (images.radial + modes.radial) - nearest.radial;
+    Dz = (images.axial + modes.axial) - nearest.axial;
 }
 
 __global__ void s1r2_ewald_table_kernel(const S1R2EwaldParams p, double *__restrict__ table) {

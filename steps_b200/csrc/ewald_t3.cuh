@@ -8,7 +8,8 @@
 //     F_rec  = - sum_h k (4 pi / V) exp(-k^2 / 4 a^2) sin(k.r) / k^2,               k = 2 pi h / L, |k| <= rec_cut
 //     F_newton = - r / |r|^3
 // and the other 47 images of the point are filled by the octahedral symmetry of the cube.
-// One thread per wedge point; the two lattice sums run in the reference's index order inside the thread, so the value of
+// One thread per wedge point; the two lattice sums run in the reference's index order inside the thread over lists prepared on
+// the host (translations n L; wave vectors with their point-independent amplitudes, skipped modes dropped), so the value of
 // an entry differs from the reference's only by the last bits of erfc/exp/sin (CUDA math library vs glibc).  The images
 // are written in the reference's order (24 proper rotations, each followed by its inversion; last write wins on the
 // symmetry planes, where several images coincide).  Note the reference's convention, kept here: rec_cut is compared with
@@ -62,60 +63,94 @@ __host__ __device__ inline CubeRot cube_rotation(int q) {
     return r;
 }
 
+// What a lattice sum needs per term, hoisted out of the per-point loops and prepared once on the host (t3_ewald_prepare):
+//   real space: the translation n L itself;
+//   reciprocal space: the wave vector k = 2 pi h / L and the point-independent amplitude vector -k (4 pi / V) exp(-k^2/4a^2) / k^2,
+//   with the modes the reference skips (h = 0, |k| beyond the cut) already dropped.  List order = the reference's summation order.
+struct LatticeShift {
+    double sx, sy, sz;
+};
+struct RecipMode {
+    double kx, ky, kz;
+    double ax, ay, az;
+};
+
 struct T3EwaldParams {
     int ngrid;
     double L, alpha, rel_cut, rec_cut;
-    int n_real, n_rec;
+    int n_real, n_rec;  // entries of the prepared lists
 };
 
-// D(r) at one separation (ewald_space.cc:198-286), sums in list order
-__host__ __device__ inline void t3_ewald_point(const double r[3], const T3EwaldParams &p, const EwaldIdx *__restrict__ real_idx,
-                                               const EwaldIdx *__restrict__ rec_idx, double D[3]) {
+inline void t3_ewald_prepare(T3EwaldParams &p, std::vector<LatticeShift> &shifts, std::vector<RecipMode> &modes) {
     const double pi = 3.14159265358979323846;
-    const double L = p.L, alpha = p.alpha;
-    const double V = L * L * L;
-    const double two_alpha_over_sqrtpi = 2.0 * alpha / sqrt(pi);
-    const double fourpi_over_V = (4.0 * pi) / V;
-    const double relcutL2 = (p.rel_cut * L) * (p.rel_cut * L);
-    double fr[3] = {0.0, 0.0, 0.0}, fk[3] = {0.0, 0.0, 0.0};
-    for (int m = 0; m < p.n_real; ++m) {
-        const EwaldIdx n = real_idx[m];
-        const double Rx = r[0] + (double)n.x * L, Ry = r[1] + (double)n.y * L, Rz = r[2] + (double)n.z * L;
-        const double R2 = Rx * Rx + Ry * Ry + Rz * Rz;
-        if (R2 == 0.0 || R2 > relcutL2) continue;
-        const double R = sqrt(R2);
-        const double invR = 1.0 / R;
-        const double invR3 = invR * invR * invR;
-        const double bracket = erfc(alpha * R) + two_alpha_over_sqrtpi * R * exp(-(alpha * alpha) * R2);
-        const double coeff = invR3 * bracket;
-        fr[0] += -Rx * coeff;
-        fr[1] += -Ry * coeff;
-        fr[2] += -Rz * coeff;
-    }
-    const double factor = 2.0 * pi / L;
-    for (int m = 0; m < p.n_rec; ++m) {
-        const EwaldIdx h = rec_idx[m];
+    std::vector<EwaldIdx> real_idx, rec_idx;
+    build_ewald_space(p.rel_cut + 1.0, real_idx);  // main.cc:467-468
+    build_ewald_space(p.rec_cut + 2.0, rec_idx);
+    shifts.clear();
+    for (const EwaldIdx &n : real_idx) shifts.push_back({(double)n.x * p.L, (double)n.y * p.L, (double)n.z * p.L});
+    modes.clear();
+    const double unit_k = 2.0 * pi / p.L;
+    const double volume_factor = (4.0 * pi) / (p.L * p.L * p.L);
+    for (const EwaldIdx &h : rec_idx) {
         if (h.x == 0 && h.y == 0 && h.z == 0) continue;
-        const double kx = factor * (double)h.x, ky = factor * (double)h.y, kz = factor * (double)h.z;
+        const double kx = unit_k * (double)h.x, ky = unit_k * (double)h.y, kz = unit_k * (double)h.z;
         const double k2 = kx * kx + ky * ky + kz * kz;
         if (k2 == 0.0 || k2 > p.rec_cut * p.rec_cut) continue;
-        const double damp = exp(-k2 / (4.0 * alpha * alpha));
-        const double coeff = fourpi_over_V * damp / k2;
-        const double s = sin(kx * r[0] + ky * r[1] + kz * r[2]);
-        fk[0] += -kx * coeff * s;
-        fk[1] += -ky * coeff * s;
-        fk[2] += -kz * coeff * s;
+        const double amp = volume_factor * exp(-k2 / (4.0 * p.alpha * p.alpha)) / k2;
+        modes.push_back({kx, ky, kz, -kx * amp, -ky * amp, -kz * amp});
     }
+    p.n_real = (int)shifts.size();
+    p.n_rec = (int)modes.size();
+}
+
+// short-range part: the screened Newtonian pull of every lattice image within rel_cut L of the point
+__host__ __device__ inline void t3_ewald_real_part(const double r[3], const T3EwaldParams &p, const LatticeShift *__restrict__ shifts, double out[3]) {
+    const double two_a_over_sqrtpi = 2.0 * p.alpha / sqrt(3.14159265358979323846);
+    const double a2 = p.alpha * p.alpha;
+    const double reach2 = (p.rel_cut * p.L) * (p.rel_cut * p.L);
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for (int m = 0; m < p.n_real; ++m) {
+        const LatticeShift s = shifts[m];
+        const double X = r[0] + s.sx, Y = r[1] + s.sy, Z = r[2] + s.sz;
+        const double d2 = X * X + Y * Y + Z * Z;
+        if (d2 == 0.0 || d2 > reach2) continue;
+        const double d = sqrt(d2);
+        const double inv = 1.0 / d;
+        const double screened = (inv * inv * inv) * (erfc(p.alpha * d) + two_a_over_sqrtpi * d * exp(-a2 * d2));
+        fx += -X * screened;
+        fy += -Y * screened;
+        fz += -Z * screened;
+    }
+    out[0] = fx; out[1] = fy; out[2] = fz;
+}
+
+// long-range part: one sine per surviving mode times its prepared amplitude vector
+__host__ __device__ inline void t3_ewald_recip_part(const double r[3], const T3EwaldParams &p, const RecipMode *__restrict__ modes, double out[3]) {
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for (int m = 0; m < p.n_rec; ++m) {
+        const RecipMode q = modes[m];
+        const double s = sin(q.kx * r[0] + q.ky * r[1] + q.kz * r[2]);
+        fx += q.ax * s;
+        fy += q.ay * s;
+        fz += q.az * s;
+    }
+    out[0] = fx; out[1] = fy; out[2] = fz;
+}
+
+// D(r) = periodic force - Newtonian force of the nearest image (ewald_space.cc:198-286); zero at the origin by definition
+__host__ __device__ inline void t3_ewald_point(const double r[3], const T3EwaldParams &p, const LatticeShift *__restrict__ shifts,
+                                               const RecipMode *__restrict__ modes, double D[3]) {
     const double r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-    if (r2 > 0.0) {
-        const double rn = sqrt(r2);
-        const double invr3 = 1.0 / (rn * rn * rn);
-        D[0] = (fr[0] + fk[0]) - (-r[0] * invr3);
-        D[1] = (fr[1] + fk[1]) - (-r[1] * invr3);
-        D[2] = (fr[2] + fk[2]) - (-r[2] * invr3);
-    } else {
+    if (!(r2 > 0.0)) {
         D[0] = D[1] = D[2] = 0.0;
+        return;
     }
+    double near_part[3], far_part[3];
+    t3_ewald_real_part(r, p, shifts, near_part);
+    t3_ewald_recip_part(r, p, modes, far_part);
+    const double rn = sqrt(r2);
+    const double inv3 = 1.0 / (rn * rn * rn);
+    for (int c = 0; c < 3; ++c) D[c] = (near_part[c] + far_part[c]) - (-r[c] * inv3);
 }
 
 __host__ __device__ inline double t3_cell_centre(int i, double h, double L) {
@@ -128,8 +163,8 @@ __host__ __device__ inline double t3_cell_centre(int i, double h, double L) {
 }
 
 // value at wedge point (i,j,k) and its images under the cube group (ewald_space.cc:316-376)
-__host__ __device__ inline void t3_ewald_fill(int i, int j, int k, const T3EwaldParams &p, const EwaldIdx *__restrict__ real_idx,
-                                              const EwaldIdx *__restrict__ rec_idx, double *__restrict__ table) {
+__host__ __device__ inline void t3_ewald_fill(int i, int j, int k, const T3EwaldParams &p, const LatticeShift *__restrict__ shifts,
+                                              const RecipMode *__restrict__ modes, double *__restrict__ table) {
     const int N = p.ngrid;
     const double h = p.L / (double)N;
     // cell-centre coordinate (i + 1/2) h - L/2, product and difference rounded separately as in the reference build.  A fused
@@ -137,7 +172,7 @@ __host__ __device__ inline void t3_ewald_fill(int i, int j, int k, const T3Ewald
     // that turns D = 0 (ewald_space.cc:280-283) into the difference of two terms of size 1/r^2 = 1e30.
     const double r[3] = {t3_cell_centre(i, h, p.L), t3_cell_centre(j, h, p.L), t3_cell_centre(k, h, p.L)};
     double Dw[3];
-    t3_ewald_point(r, p, real_idx, rec_idx, Dw);
+    t3_ewald_point(r, p, shifts, modes, Dw);
     auto at = [N](int a, int b, int c) { return ((size_t)((a * N + b) * N + c)) * 3u; };
     {
         const size_t o = at(i, j, k);
@@ -163,10 +198,10 @@ __host__ __device__ inline void t3_ewald_fill(int i, int j, int k, const T3Ewald
 
 // one thread per wedge point; points = packed (i, j, k) triples
 __global__ void t3_ewald_table_kernel(const int *__restrict__ points, int n_points, const T3EwaldParams p,
-                                      const EwaldIdx *__restrict__ real_idx, const EwaldIdx *__restrict__ rec_idx, double *__restrict__ table) {
+                                      const LatticeShift *__restrict__ shifts, const RecipMode *__restrict__ modes, double *__restrict__ table) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_points) return;
-    t3_ewald_fill(points[3 * t], points[3 * t + 1], points[3 * t + 2], p, real_idx, rec_idx, table);
+    t3_ewald_fill(points[3 * t], points[3 * t + 1], points[3 * t + 2], p, shifts, modes, table);
 }
 
 }  // namespace steps

@@ -33,7 +33,7 @@ __host__ __device__ __forceinline__ void pair_exact_unit(const TopoParams &tp, T
             tx = w * dx; ty = w * dy; tz = w * dz;
         } else {
             T D[3];
-            t3_interpolate<T>(tp.dim0, L, static_cast<const T *>(tp.table), dx, dy, dz, D);
+            t3_correction_rowmajor<T>(t3_lookup_of<T>(tp), dx, dy, dz, D);
             tx = w * dx - D[0];
             ty = w * dy - D[1];
             tz = w * dz - D[2];
@@ -59,38 +59,11 @@ __host__ __device__ __forceinline__ void pair_exact_unit(const TopoParams &tp, T
 // Same quantities as pair_exact_unit<T, 1> with cheaper instruction sequences; every substitution moves a result by a few ulp at
 // most (tolerance of the path: 1e-12):
 //   * nearest image by d -= copysign(L, d) instead of d - L*d/|d| (a division whose quotient is +-1 up to one rounding of L*d);
-//   * cell coordinate u = (d + L/2) * (N/L) - 1/2 instead of two divisions per axis;
-//   * cell indices wrapped by compare-and-add instead of integer modulo (general modulo kept for coordinates outside one period);
 //   * r^-3 = rsqrt(r2)^3 for r safely outside the softening length, the exact branches of force_softening otherwise;
-//   * the 4x4x4 contraction z first (16 rows x 12 FMA, then 16 x 3 FMA with w_x w_y): 256 instead of 272 FP64 instructions.
-struct T3Fast {
-    double L, halfL, inv_h;
-    int N;
-};
-
+//   * the correction from the z-window copy of the table with 128-bit loads (t3_correction_zwin, t3_lookup.cuh).
 template <typename T>
-__host__ __device__ __forceinline__ void t3_fast_axis(T d, T halfL, T inv_h, int N, int (&idx)[4], T (&w)[4]) {
-    const T u = (d + halfL) * inv_h - (T)0.5;
-    const T uf = floor(u);
-    int i0 = (int)uf;
-    i0 = i0 < 0 ? i0 + N : i0;
-    i0 = i0 >= N ? i0 - N : i0;
-    if ((unsigned)i0 >= (unsigned)N) i0 = imodp((int)uf, N);  // coordinates outside one period (a caller that did not wrap)
-    cubic_weights<T>((T)(u - uf), w);
-    int v = i0 - 1;
-    v = v < 0 ? v + N : v;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        idx[k] = v;
-        v = (v + 1 == N) ? 0 : v + 1;
-    }
-}
-
-template <typename T>
-__host__ __device__ __forceinline__ void pair_t3_fast_unit(const T3Fast &k, const T *__restrict__ table, T xi, T yi, T zi, T si, T xj, T yj, T zj, T sj,
-                                                  T &tx, T &ty, T &tz) {
-    const T L = (T)k.L, halfL = (T)k.halfL, inv_h = (T)k.inv_h;
-    const int N = k.N;
+__host__ __device__ __forceinline__ void pair_t3_fast_unit(const T3Lookup &k, T xi, T yi, T zi, T si, T xj, T yj, T zj, T sj, T &tx, T &ty, T &tz) {
+    const T L = (T)k.L, halfL = (T)k.halfL;
     T dx = xj - xi, dy = yj - yi, dz = zj - zi;
     if (fabs(dx) > halfL) dx -= copysign(L, dx);
     if (fabs(dy) > halfL) dy -= copysign(L, dy);
@@ -104,42 +77,11 @@ __host__ __device__ __forceinline__ void pair_t3_fast_unit(const T3Fast &k, cons
     } else {
         w = softened_w<T>(sqrt(r2), beta);
     }
-    int ix[4], iy[4], iz[4];
-    T wx[4], wy[4], wz[4];
-    t3_fast_axis<T>(dx, halfL, inv_h, N, ix, wx);
-    t3_fast_axis<T>(dy, halfL, inv_h, N, iy, wy);
-    t3_fast_axis<T>(dz, halfL, inv_h, N, iz, wz);
-    int zo[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) zo[c] = 3 * iz[c];
-    T s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int rx = ix[a] * N;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const T *__restrict__ row = table + (size_t)(rx + iy[b]) * (size_t)(3 * N);
-            T p0, p1, p2;
-            {
-                const T *__restrict__ e = row + zo[0];
-                p0 = wz[0] * table_ld(e); p1 = wz[0] * table_ld(e + 1); p2 = wz[0] * table_ld(e + 2);
-            }
-#pragma unroll
-            for (int c = 1; c < 4; ++c) {
-                const T *__restrict__ e = row + zo[c];
-                p0 = fma(wz[c], table_ld(e), p0);
-                p1 = fma(wz[c], table_ld(e + 1), p1);
-                p2 = fma(wz[c], table_ld(e + 2), p2);
-            }
-            const T wxy = wx[a] * wy[b];
-            s0 = fma(wxy, p0, s0);
-            s1 = fma(wxy, p1, s1);
-            s2 = fma(wxy, p2, s2);
-        }
-    }
-    tx = fma(w, dx, -s0);
-    ty = fma(w, dy, -s1);
-    tz = fma(w, dz, -s2);
+    T D[3];
+    t3_correction_zwin<T>(k, dx, dy, dz, D);
+    tx = fma(w, dx, -D[0]);
+    ty = fma(w, dy, -D[1]);
+    tz = fma(w, dz, -D[2]);
 }
 
 // shared memory of this kernel besides the window of j-side accumulators (pair_r3_sym.cuh: sym_window_tiles)
@@ -191,11 +133,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const 
     int nsym = 0;
     int K0 = 0;  // tiles streamed so far by this CTA (pipeline stage / parity bookkeeping, pair_r3_sym.cuh)
     static_assert(!FAST || TOPO == 1, "lean arithmetic exists for T^3 only");
-    T3Fast fk;
-    fk.L = (double)(T)tp.L;
-    fk.halfL = (double)((T)0.5 * (T)tp.L);
-    fk.inv_h = (double)((T)tp.dim0 / (T)tp.L);
-    fk.N = tp.dim0;
+    const T3Lookup fk = t3_lookup_of<T>(tp);
     // (the engine launches the FAST instantiation only for IS_PERIODIC >= 2: the nearest-image-only sum has no table)
 
     for (int w0 = TA; w0 < TB; w0 += WB) {
@@ -276,7 +214,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const 
                         for (int r = 0; r < R; ++r) {
                             T tx, ty, tz;
                             if (FAST)
-                                pair_t3_fast_unit<T>(fk, static_cast<const T *>(tp.table), xi[r], yi[r], zi[r], si[r], (T)q.x, (T)q.y, (T)q.z, (T)q.s, tx, ty, tz);
+                                pair_t3_fast_unit<T>(fk, xi[r], yi[r], zi[r], si[r], (T)q.x, (T)q.y, (T)q.z, (T)q.s, tx, ty, tz);
                             else
                                 pair_exact_unit<T, TOPO>(tp, xi[r], yi[r], zi[r], si[r], (T)q.x, (T)q.y, (T)q.z, (T)q.s, tx, ty, tz);
                             const T mj = (T)q.m;

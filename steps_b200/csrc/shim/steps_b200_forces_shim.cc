@@ -9,7 +9,8 @@
 //     void recalculate_softening()                                         forces_cuda.cu:868-875
 // so step.cc:191-197 and main.cc:1581-1607 link against it unchanged.  The globals the reference
 // kernels read at link time are packed into steps_b200_params on every call (they are scalars and
-// pointers; the tables themselves are uploaded once and cached by pointer identity).
+// pointers; the device buffers are cached between calls, the tables are uploaded again on every call,
+// as the reference does, because a caller may hand in different contents at the same address).
 //
 // Error convention of the reference (forces_cuda.cu:970-974, main.cc:1851-1856): message on stderr,
 // ForceError = true, return.  There is no CPU fallback.

@@ -96,6 +96,17 @@ bool ensure_resident(REAL *xx, REAL *vv, REAL *FF) {
     if (const char *so = getenv("STEPS_B200_SPATIAL_ORDER"))
         if (atoi(so) > 0 && steps_b200_group_set_spatial_order(g_group, atoi(so))) return fail("spatial order");
     if (steps_b200_group_upload(g_group, xx, vv, M, SOFT_LENGTH, FF)) return fail("state upload");
+    // the initial force evaluation of main.cc went through the stateless forces() call, whose cached engines (particle state, partial-sum
+    // and row buffers) are not needed any more: the resident group owns the devices from here on
+    steps_b200_release_cached();
+    // a snapshot still being written when the process ends must reach the disk: join the writer thread at exit
+    static bool registered = false;
+    if (!registered) {
+        registered = true;
+        atexit([] {
+            if (g_group) steps_b200_group_snapshot_wait(g_group);
+        });
+    }
     return true;
 }
 }  // namespace

@@ -35,16 +35,27 @@ static double rel(const double a[3], const double b[3]) {
     return s > 0 ? d / s : d;
 }
 
+// the aligned row copies of a T^3 table (t3_lookup.cuh), built on the host with the function the device kernel runs per (copy, row)
+template <int TOPO>
+static std::vector<double> zwin_copy(TopoParams &tp) {
+    std::vector<double> zw;
+    if (TOPO == 1 && tp.is_periodic >= 2 && tp.table) {
+        const int N = tp.dim0;
+        zw.resize(t3_aligned_elems<double>(N));
+        for (int c = 0; c < t3_copies<double>(); ++c)
+            for (size_t row = 0; row < (size_t)N * N; ++row) t3_aligned_fill<double>(static_cast<const double *>(tp.table), N, c, row, zw.data());
+        tp.table_zwin = zw.data();
+    }
+    return zw;
+}
+
 template <int TOPO>
 static int run(TopoParams tp, int n_pairs, unsigned seed, double soft, double box_xy) {
     std::mt19937_64 rng(seed);
     std::uniform_real_distribution<double> U(0.0, 1.0);
     double e1 = 0, e2 = 0, e3 = 0;
-    T3Fast fk;
-    fk.L = tp.L;
-    fk.halfL = 0.5 * tp.L;
-    fk.inv_h = (double)tp.dim0 / tp.L;
-    fk.N = tp.dim0;
+    const std::vector<double> zw = zwin_copy<TOPO>(tp);
+    const T3Lookup fk = t3_lookup_of<double>(tp);
     for (int p = 0; p < n_pairs; ++p) {
         double xi[3], xj[3];
         for (int k = 0; k < 3; ++k) {
@@ -65,7 +76,7 @@ static int run(TopoParams tp, int n_pairs, unsigned seed, double soft, double bo
         e2 = std::fmax(e2, rel(neg, t));
         if (TOPO == 1 && tp.is_periodic >= 2) {
             double tf[3];
-            pair_t3_fast_unit<double>(fk, static_cast<const double *>(tp.table), xi[0], xi[1], xi[2], si, xj[0], xj[1], xj[2], sj, tf[0], tf[1], tf[2]);
+            pair_t3_fast_unit<double>(fk, xi[0], xi[1], xi[2], si, xj[0], xj[1], xj[2], sj, tf[0], tf[1], tf[2]);
             e3 = std::fmax(e3, rel(tf, t));
         }
     }
@@ -81,11 +92,8 @@ static int forces_sym(TopoParams tp, const char *state_path, int n, bool lean, c
     const std::vector<double> st = load(state_path);
     if ((int)st.size() != 5 * n) return 6;
     const double *x = st.data(), *M = x + 3 * n, *S = M + n;
-    T3Fast fk;
-    fk.L = tp.L;
-    fk.halfL = 0.5 * tp.L;
-    fk.inv_h = tp.dim0 > 0 ? (double)tp.dim0 / tp.L : 0.0;
-    fk.N = tp.dim0;
+    const std::vector<double> zw = zwin_copy<TOPO>(tp);
+    const T3Lookup fk = t3_lookup_of<double>(tp);
     std::vector<double> F(3 * (size_t)n, 0.0);
     for (int i = 0; i < n; ++i) {
         pair_exact<double, TOPO>(tp, x[3 * i], x[3 * i + 1], x[3 * i + 2], S[i], x[3 * i], x[3 * i + 1], x[3 * i + 2], M[i], S[i], F[3 * i], F[3 * i + 1],
@@ -93,7 +101,7 @@ static int forces_sym(TopoParams tp, const char *state_path, int n, bool lean, c
         for (int j = i + 1; j < n; ++j) {
             double t[3];
             if (TOPO == 1 && lean)
-                pair_t3_fast_unit<double>(fk, static_cast<const double *>(tp.table), x[3 * i], x[3 * i + 1], x[3 * i + 2], S[i], x[3 * j], x[3 * j + 1],
+                pair_t3_fast_unit<double>(fk, x[3 * i], x[3 * i + 1], x[3 * i + 2], S[i], x[3 * j], x[3 * j + 1],
                                           x[3 * j + 2], S[j], t[0], t[1], t[2]);
             else
                 pair_exact_unit<double, TOPO>(tp, x[3 * i], x[3 * i + 1], x[3 * i + 2], S[i], x[3 * j], x[3 * j + 1], x[3 * j + 2], S[j], t[0], t[1], t[2]);

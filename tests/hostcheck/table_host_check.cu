@@ -26,10 +26,10 @@ int main(int argc, char **argv) {
     if (!strcmp(argv[1], "t3") && argc == 7) {
         const int ngrid = atoi(argv[2]);
         const double L = atof(argv[3]), rel = atof(argv[4]), rec = atof(argv[5]);
-        std::vector<EwaldIdx> re, rc;
-        build_ewald_space(rel + 1.0, re);
-        build_ewald_space(rec + 2.0, rc);
-        const T3EwaldParams p{ngrid, L, 2.0 / L, rel, rec, (int)re.size(), (int)rc.size()};
+        T3EwaldParams p{ngrid, L, 2.0 / L, rel, rec, 0, 0};
+        std::vector<LatticeShift> re;
+        std::vector<RecipMode> rc;
+        t3_ewald_prepare(p, re, rc);
         std::vector<double> tab((size_t)ngrid * ngrid * ngrid * 3, 0.0);
 #pragma omp parallel for schedule(dynamic)
         for (int i = ngrid / 2; i < ngrid; ++i)

@@ -118,3 +118,62 @@ def test_library_calls_restore_the_callers_current_device():
         assert torch.cuda.current_device() == 1
     finally:
         torch.cuda.set_device(0)
+
+
+def _group_forces_and_steps(c, k, nsteps=2):
+    g = c.g
+    REAL = g.REAL
+    n = g.N
+    grp = Group(g, k)
+    lib = grp.lib
+    _lib.check(lib.steps_b200_group_upload(grp.h, c.x.ctypes.data, c.v.ctypes.data, g.M.ctypes.data, g.SOFT_LENGTH.ctypes.data, None))
+    _lib.check(lib.steps_b200_group_forces(grp.h))
+    sym = [bool(lib.steps_b200_engine_is_symmetric(C.c_void_p(lib.steps_b200_group_engine(grp.h, d)))) for d in range(k)]
+    F0 = np.empty(3 * n, dtype=REAL)
+    _lib.check(lib.steps_b200_group_download(grp.h, None, None, F0.ctypes.data))
+    a = g.a_start
+    H = sb.CALCULATE_Hubble_param(g, a)
+    em = C.c_double()
+    _lib.check(lib.steps_b200_group_init_errmax(grp.h, a, H, C.byref(em)))
+    h = (2 * g.ACC_PARAM / em.value) ** 0.5
+    errs = []
+    for _ in range(nsteps):
+        an = sb.friedmann_solver_step(g, a, h)
+        Hn = sb.CALCULATE_Hubble_param(g, an)
+        _lib.check(lib.steps_b200_group_kdk_step(grp.h, h, a, H, an, Hn, C.byref(em)))
+        a, H = an, Hn
+        errs.append(em.value)
+    x, v, F = (np.empty(3 * n, dtype=REAL) for _ in range(3))
+    _lib.check(lib.steps_b200_group_download(grp.h, x.ctypes.data, v.ctypes.data, F.ctypes.data))
+    grp.close()
+    return sym, F0, h, errs, x, v, F
+
+
+@pytest.mark.parametrize("k", [2, 4, 8])
+@pytest.mark.parametrize("case", ["r3_f64", "r3_f32", "s1r2nl"])
+def test_group_action_reaction_over_k_gpus(case, k):
+    """the action-reaction evaluation split over k GPUs (ring assignment of block pairs, NCCL all-gather of positions and
+    all-reduce of the j-side sums) against one GPU: initial forces, the first time step and two KDK steps"""
+    if ndev() < k:
+        pytest.skip(f"needs {k} GPUs")
+    if case == "r3_f64":
+        c = ic.compactified_r3(40000, 64, 500, 52, d_s=105.0)
+    elif case == "r3_f32":
+        c = ic.compactified_r3(40000, 64, 500, 53, np.float32, d_s=105.0)
+    else:
+        from oracle import pyref
+
+        if not pyref.available("s1r2nl_f64"):
+            pytest.skip("radial table needs oracle/_ref")
+        c = ic.s1r2_cylinder(24000, 24, 600, 54, lookup=False, is_periodic=2, L=20.0, r_sim=60.0, d_s=10.0, r_crit=15.0)
+        sb.get_cylindrical_force_table(c.g, 400, 0)
+    tol = 1e-12 if c.g.REAL == np.float64 else 2e-5
+    sym1, F0a, ha, ea, xa, va, Fa = _group_forces_and_steps(c, 1)
+    symk, F0b, hb, eb, xb, vb, Fb = _group_forces_and_steps(c, k)
+    assert all(sym1) and all(symk), "the action-reaction path must be the one that runs"
+    scale = np.abs(F0a.astype(np.float64)).max()
+    assert np.abs(F0a.astype(np.float64) - F0b).max() / scale < tol
+    assert abs(ha - hb) <= (1e-12 if c.g.REAL == np.float64 else 1e-4) * ha
+    assert np.allclose(ea, eb, rtol=1e-10 if c.g.REAL == np.float64 else 1e-3)
+    assert np.abs(xa.astype(np.float64) - xb).max() / c.g.Rsim < (1e-13 if c.g.REAL == np.float64 else 1e-5)
+    assert np.abs(Fa.astype(np.float64) - Fb).max() / scale < tol

@@ -551,19 +551,21 @@ def run_ours(args, out_fd):
         h2d = 3 * N * rb
 
     log(f"[bench] rank {rank}: timed steps done ({ms_step:.1f} ms/step), e2e leg ...")
-    e2e_call()  # first call: creates the cached engine of the stateless path / warms the collective path
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_call()  # synchronous: returns after the D2H of F
-    t_e2e = time.perf_counter() - t0
-    barrier()
-    t_e2e = max_over_ranks(t_e2e)
-    e2e_value = args.steps * N * float(N) / t_e2e
-    d2h = 3 * (hi - lo + 1) * rb
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(float(h2d))),
-           "d2h_bytes_per_step": int(sum_over_ranks(float(d2h))), "ms_per_step": 1e3 * t_e2e / args.steps, "call": e2e_desc}
-    launches_e2e = 4 * args.steps  # pack + pair + reduce + tile_smax per call (lower bound: the action-reaction path adds one row reduction per pass)
+    e2e, launches_e2e = None, 0
+    if not args.no_e2e:
+        e2e_call()  # first call: creates the cached engine of the stateless path / warms the collective path
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_call()  # synchronous: returns after the D2H of F
+        t_e2e = time.perf_counter() - t0
+        barrier()
+        t_e2e = max_over_ranks(t_e2e)
+        e2e_value = args.steps * N * float(N) / t_e2e
+        d2h = 3 * (hi - lo + 1) * rb
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(float(h2d))),
+               "d2h_bytes_per_step": int(sum_over_ranks(float(d2h))), "ms_per_step": 1e3 * t_e2e / args.steps, "call": e2e_desc}
+        launches_e2e = 4 * args.steps  # pack + pair + reduce + tile_smax per call (lower bound: the action-reaction path adds one row reduction per pass)
 
     cpu, parity, refcuda, fn_pack = None, None, None, None
     if not args.no_parity or (rank == 0 and world == 1 and not args.no_cpu):

@@ -15,6 +15,7 @@
 #include <dlfcn.h>
 #include <cuda_runtime.h>
 #include <nccl.h>  // types and enums only; the library itself is dlopen'ed at comm_init time
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler injects its library
 
 #include "../../include/steps_b200.h"
 #include "aux_kernels.cuh"
@@ -104,6 +105,12 @@ int nccl_load() {
 
 // Every entry point that selects a device restores the caller's current device on return: a host program (PyTorch, an MPI
 // rank driving its own GPU) must not find its CUDA context switched by a library call.
+// NVTX range on the host thread that enqueues a phase (nsys / ncu --nvtx attribute the launches inside to it)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct DeviceGuard {
     int prev = -1;
     DeviceGuard() {
@@ -468,7 +475,7 @@ bool s1r2_sym_env_default() {
 }
 // Shapes of the action-reaction kernel of the table-lookup topologies (pair_generic_sym.cuh); STEPS_B200_GEN_SYM_VARIANT=k
 // (the `unroll` field selects the arithmetic here: 0 = the reference's operations one by one, 1 = the lean T^3 sequence of
-// pair_t3_fast_unit; the S^1xR^2 lookup build always runs the exact one)
+// pair_t3_fast_unit, 2 = lean + software prefetch of the table rows; the S^1xR^2 lookup build always runs the exact one)
 constexpr SymVariant GEN_SYM_VARIANTS[] = {
     {2, 128, 3, 0},  // 0: i-block 256, <= 168 registers
     {2, 128, 4, 0},  // 1: i-block 256, <= 128 registers (the one-sided kernel's budget)
@@ -476,6 +483,9 @@ constexpr SymVariant GEN_SYM_VARIANTS[] = {
     {2, 128, 3, 1},  // 3: shape 0, lean T^3 arithmetic
     {2, 128, 4, 1},  // 4: shape 1, lean T^3 arithmetic
     {3, 128, 2, 1},  // 5: i-block 384, <= 255 registers, lean T^3 arithmetic
+    {3, 128, 2, 2},  // 6: shape 5 + software prefetch of the next pair's table rows into L1
+    {2, 128, 3, 2},  // 7: shape 3 + prefetch
+    {2, 128, 4, 2},  // 8: shape 4 + prefetch
 };
 constexpr int N_GEN_SYM_VARIANTS = sizeof(GEN_SYM_VARIANTS) / sizeof(GEN_SYM_VARIANTS[0]);
 int gen_sym_variant() {
@@ -984,21 +994,21 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     } break;
         if (gen_sym_topology(e)) {
             const int base_gen = sym_base_generic(nwarps, GEN_STAGES, (int)sizeof(JRec), (int)sizeof(T), GEN_TJ);
-            const size_t smem_gen = (size_t)base_gen + (size_t)sym_window_tiles(sv.minb, base_gen, (int)sizeof(T), GEN_TJ) * 3 * GEN_TJ * sizeof(T);
+            const size_t smem_gen = (size_t)base_gen + (size_t)gen_sym_window(e->p.topology == STEPS_TOPO_T3 ? 1 : 2, sv.minb, base_gen, (int)sizeof(T), GEN_TJ) * 3 * GEN_TJ * sizeof(T);
 #define LAUNCH_GEN_SYM_VT(V, TOPO, FASTV)                                                                                                \
     {                                                                                                                               \
         auto kern = force_generic_sym_kernel<T, TOPO, GEN_SYM_VARIANTS[V].R, GEN_SYM_VARIANTS[V].threads, GEN_TJ, GEN_STAGES,       \
-                                             GEN_SYM_VARIANTS[V].minb, FASTV>;                                                      \
+                                             GEN_SYM_VARIANTS[V].minb, FASTV, (FASTV) && GEN_SYM_VARIANTS[V].unroll == 2>;          \
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gen));                             \
         kern<<<n_cta, GEN_SYM_VARIANTS[V].threads, smem_gen, e->stream>>>(sa, e->tp);                                    \
     }
 #define LAUNCH_GEN_SYM_V(V)                                                   \
     case V:                                                                   \
-        if (e->p.topology == STEPS_TOPO_T3 && GEN_SYM_VARIANTS[V].unroll == 1 && e->p.is_periodic >= 2) LAUNCH_GEN_SYM_VT(V, 1, true) \
+        if (e->p.topology == STEPS_TOPO_T3 && GEN_SYM_VARIANTS[V].unroll >= 1 && e->p.is_periodic >= 2) LAUNCH_GEN_SYM_VT(V, 1, true) \
         else if (e->p.topology == STEPS_TOPO_T3) LAUNCH_GEN_SYM_VT(V, 1, false) \
         else LAUNCH_GEN_SYM_VT(V, 2, false)                                   \
         break;
-            switch (gen_sym_variant()) { LAUNCH_GEN_SYM_V(0) LAUNCH_GEN_SYM_V(1) LAUNCH_GEN_SYM_V(2) LAUNCH_GEN_SYM_V(3) LAUNCH_GEN_SYM_V(4) LAUNCH_GEN_SYM_V(5) }
+            switch (gen_sym_variant()) { LAUNCH_GEN_SYM_V(0) LAUNCH_GEN_SYM_V(1) LAUNCH_GEN_SYM_V(2) LAUNCH_GEN_SYM_V(3) LAUNCH_GEN_SYM_V(4) LAUNCH_GEN_SYM_V(5) LAUNCH_GEN_SYM_V(6) LAUNCH_GEN_SYM_V(7) LAUNCH_GEN_SYM_V(8) }
 #undef LAUNCH_GEN_SYM_V
 #undef LAUNCH_GEN_SYM_VT
         } else if (F64 && e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP) {
@@ -1041,6 +1051,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     CU_TRY(cudaEventRecord(e->ev[5], e->stream));
     // multi-GPU: the j-side sums a rank formed for other ranks' particles travel in ONE all-reduce (3 n_pad REALs).
     // (An engine given a rank without a communicator -- the single-GPU test hook -- skips it: the test sums on the host.)
+    NvtxRange nvtx_ar_("steps_b200:allreduce(j-side sums)+final reduce");
     if (e->nranks > 1 && e->comm)
         NCCL_TRY(g_nccl.AllReduce(e->d_fsym, e->d_fsym, (size_t)3 * e->n_pad, F64 ? ncclFloat64 : ncclFloat32, ncclSum, e->comm, e->stream));
     return finish_pair_sym(e, id_min, n_i, pl);
@@ -1070,8 +1081,12 @@ int forces_impl(steps_b200_engine *e, int id_min, int id_max) {
     if (id_min < 0 || id_max >= e->n || id_max < id_min) return fail("bad [id_min, id_max]");
     DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
+    NvtxRange nvtx_("steps_b200:forces");
     CU_TRY(cudaEventRecord(e->ev[0], e->stream));
-    if (pack(e)) return 1;
+    {
+        NvtxRange r_("steps_b200:pack");
+        if (pack(e)) return 1;
+    }
     Plan pl;
     const int n_i = id_max - id_min + 1;
     int rc;
@@ -1084,6 +1099,7 @@ int forces_impl(steps_b200_engine *e, int id_min, int id_max) {
         CU_TRY(cudaStreamSynchronize(e->stream));
         if (zflag != 0) sym = false;
     }
+    NvtxRange nvtx_pair_(sym ? "steps_b200:pair(action-reaction)+reduce" : "steps_b200:pair(one-sided)+reduce");
     if (sym) rc = (e->real_bytes == 8) ? launch_pair_sym<double>(e, id_min, n_i, pl) : launch_pair_sym<float>(e, id_min, n_i, pl);
     else rc = (e->real_bytes == 8) ? launch_pair<double>(e, id_min, n_i, pl) : launch_pair<float>(e, id_min, n_i, pl);
     if (rc) return rc;
@@ -1112,6 +1128,7 @@ KdkScalars kdk_scalars(const steps_b200_engine *e, double h, double a, double hu
 
 int gather_positions(steps_b200_engine *e) {
     if (e->nranks <= 1) return 0;
+    NvtxRange nvtx_("steps_b200:allgather(x)");
     const ncclDataType_t dt = e->real_bytes == 8 ? ncclFloat64 : ncclFloat32;
     NCCL_TRY(g_nccl.GroupStart());
     for (int r = 0; r < e->nranks; ++r) {
@@ -1469,6 +1486,7 @@ extern "C" int steps_b200_engine_kdk_step(steps_b200_engine *e, double h, double
     if (!e->have_state) return fail("engine has no particle state");
     DeviceGuard dg_;
     CU_TRY(cudaSetDevice(e->device));
+    NvtxRange nvtx_("steps_b200:kdk_step");
     CU_TRY(cudaEventRecord(e->ev[2], e->stream));
     if (e->glass)
         return e->real_bytes == 8 ? glass_kdk_step<double>(e, h, a_old, hubble_old, a_new, hubble_new, errmax_out)

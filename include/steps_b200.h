@@ -249,6 +249,11 @@ int steps_b200_spatial_order(const void *x, int n, int real_bytes, int ngrid, in
 int steps_b200_permute(const void *src, void *dst, const int *perm, int n, int width, int elem_bytes, int scatter);
 int steps_b200_group_set_spatial_order(steps_b200_group *g, int ngrid);
 int steps_b200_group_permutation(steps_b200_group *g, int *perm_out);
+/* T^3 with the Ewald table decides by itself when the caller has not (no set_spatial_order call, not even with 0): group_upload() measures
+ * order_incoherence() -- median nearest-image distance between array neighbours (sample of 4096) in units of the mean interparticle
+ * spacing, ~1 for lattice-ordered input, ~N^(1/3)/2 for a shuffled one -- and keeps the resident copy sorted by table cell when it exceeds 4.
+ * STEPS_B200_SPATIAL_ORDER=0 switches the automatic decision off. */
+double steps_b200_order_incoherence(const void *x, int n, int real_bytes, double L);
 /* ASCII snapshots in the reference's format (write_ascii_snapshot, inputoutput.cc:826-909; SURVEY.md 8f.2 -- the HDF5 formats need
  * libhdf5): per particle "x y z vx vy vz M", each "%.16f\t", x and M times H0_dimless (in REAL precision), v times sqrt(a)*UNIT_V (in
  * double), zero velocities in a GLASS_MAKING build.  snapshot_ascii_host formats host arrays with a pool of workers (nthreads <= 0: all

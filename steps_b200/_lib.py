@@ -91,6 +91,7 @@ SYMBOLS = {
     "steps_b200_group_destroy": (None, [_VP]),
     "steps_b200_group_size": (_I, [_VP]),
     "steps_b200_group_engine": (_VP, [_VP, _I]),
+    "steps_b200_order_incoherence": (_D, [_VP, _I, _I, _D]),
     "steps_b200_group_upload": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "steps_b200_group_forces": (_I, [_VP]),
     "steps_b200_group_init_errmax": (_I, [_VP, _D, _D, _PD]),

@@ -475,7 +475,7 @@ bool s1r2_sym_env_default() {
 }
 // Shapes of the action-reaction kernel of the table-lookup topologies (pair_generic_sym.cuh); STEPS_B200_GEN_SYM_VARIANT=k
 // (the `unroll` field selects the arithmetic here: 0 = the reference's operations one by one, 1 = the lean T^3 sequence of
-// pair_t3_fast_unit, 2 = lean + software prefetch of the table rows; the S^1xR^2 lookup build always runs the exact one)
+// pair_t3_fast_unit; the S^1xR^2 lookup build always runs the exact one)
 constexpr SymVariant GEN_SYM_VARIANTS[] = {
     {2, 128, 3, 0},  // 0: i-block 256, <= 168 registers
     {2, 128, 4, 0},  // 1: i-block 256, <= 128 registers (the one-sided kernel's budget)
@@ -483,10 +483,9 @@ constexpr SymVariant GEN_SYM_VARIANTS[] = {
     {2, 128, 3, 1},  // 3: shape 0, lean T^3 arithmetic
     {2, 128, 4, 1},  // 4: shape 1, lean T^3 arithmetic
     {3, 128, 2, 1},  // 5: i-block 384, <= 255 registers, lean T^3 arithmetic
-    {3, 128, 2, 2},  // 6: shape 5 + software prefetch of the next pair's table rows into L1
-    {2, 128, 3, 2},  // 7: shape 3 + prefetch
-    {2, 128, 4, 2},  // 8: shape 4 + prefetch
 };
+// (measured and dropped in round 2, profiles/r2h_t3_prefetch_sweep.txt: software prefetch of the next pair's table rows into L1 --
+// 2.6e10 against 3.2e10 pairs/s at 64^3: the extra address arithmetic and LSU instructions cost more than the latency they hide)
 constexpr int N_GEN_SYM_VARIANTS = sizeof(GEN_SYM_VARIANTS) / sizeof(GEN_SYM_VARIANTS[0]);
 int gen_sym_variant() {
     static int v = -1;
@@ -998,7 +997,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
 #define LAUNCH_GEN_SYM_VT(V, TOPO, FASTV)                                                                                                \
     {                                                                                                                               \
         auto kern = force_generic_sym_kernel<T, TOPO, GEN_SYM_VARIANTS[V].R, GEN_SYM_VARIANTS[V].threads, GEN_TJ, GEN_STAGES,       \
-                                             GEN_SYM_VARIANTS[V].minb, FASTV, (FASTV) && GEN_SYM_VARIANTS[V].unroll == 2>;          \
+                                             GEN_SYM_VARIANTS[V].minb, FASTV>;                                                      \
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gen));                             \
         kern<<<n_cta, GEN_SYM_VARIANTS[V].threads, smem_gen, e->stream>>>(sa, e->tp);                                    \
     }
@@ -1008,7 +1007,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         else if (e->p.topology == STEPS_TOPO_T3) LAUNCH_GEN_SYM_VT(V, 1, false) \
         else LAUNCH_GEN_SYM_VT(V, 2, false)                                   \
         break;
-            switch (gen_sym_variant()) { LAUNCH_GEN_SYM_V(0) LAUNCH_GEN_SYM_V(1) LAUNCH_GEN_SYM_V(2) LAUNCH_GEN_SYM_V(3) LAUNCH_GEN_SYM_V(4) LAUNCH_GEN_SYM_V(5) LAUNCH_GEN_SYM_V(6) LAUNCH_GEN_SYM_V(7) LAUNCH_GEN_SYM_V(8) }
+            switch (gen_sym_variant()) { LAUNCH_GEN_SYM_V(0) LAUNCH_GEN_SYM_V(1) LAUNCH_GEN_SYM_V(2) LAUNCH_GEN_SYM_V(3) LAUNCH_GEN_SYM_V(4) LAUNCH_GEN_SYM_V(5) }
 #undef LAUNCH_GEN_SYM_V
 #undef LAUNCH_GEN_SYM_VT
         } else if (F64 && e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP) {
@@ -1862,6 +1861,7 @@ struct steps_b200_group {
     SnapshotJob snap;  // asynchronous ASCII snapshot in flight (snapshot_io.h)
     // spatial order (opt-in): the engines hold the particles sorted by cell; perm[k] = caller's index of the k-th resident particle
     int order_ngrid = 0;
+    bool order_explicit = false;  // the caller chose (set_spatial_order, also to switch it off): no automatic decision at upload
     std::vector<int> perm;
     std::vector<char> tmp[3];  // host staging for the permuted copies
 };
@@ -1958,6 +1958,16 @@ extern "C" steps_b200_engine *steps_b200_group_engine(steps_b200_group *g, int d
 
 extern "C" int steps_b200_group_upload(steps_b200_group *g, const void *x, const void *v, const void *M, const void *soft, const void *F) {
     if (!g) return fail("group is NULL");
+    if (!g->order_explicit && !g->eng.empty() && g->eng[0]->p.topology == STEPS_TOPO_T3 && g->eng[0]->p.is_periodic >= 2 && x) {
+        // T^3 with the Ewald table: the gather of the pair kernel reads ~6x fewer cache lines when neighbours in the array are neighbours
+        // in space (measured at 48^3: 2.3e10 pairs/s lattice order, 1.2e10 sorted by table cell, 5.4e9 shuffled).  An input whose order is
+        // incoherent is therefore kept sorted by table cell on the devices; the caller's order is what upload / download / snapshots see.
+        static const char *off = getenv("STEPS_B200_SPATIAL_ORDER");
+        const bool disabled = off && atoi(off) == 0;
+        const double inc = steps_b200_order_incoherence(x, g->n, g->real_bytes, g->eng[0]->p.L);
+        g->order_ngrid = (!disabled && inc > 4.0) ? std::max(1, g->eng[0]->p.table_dim0) : 0;
+        if (g->order_ngrid == 0) g->perm.clear();
+    }
     if (g->order_ngrid > 0) {
         // resident copy sorted by cell: build the permutation from these positions, upload gathered copies
         if (!x || !M || !soft) return fail("x, M, soft must be non-NULL");
@@ -2068,8 +2078,34 @@ extern "C" int steps_b200_group_set_spatial_order(steps_b200_group *g, int ngrid
     for (auto *e : g->eng)
         if (e->have_state) return fail("set_spatial_order must precede upload");
     g->order_ngrid = ngrid;
+    g->order_explicit = true;
     g->perm.clear();
     return 0;
+}
+
+// Is the caller's particle order spatially incoherent?  Median nearest-image distance between particles that are neighbours in the
+// array (a sample of them), in units of the mean interparticle spacing: ~1 for lattice-ordered or cell-sorted input, ~N^(1/3)/2 for a
+// shuffled one.  Host-only, pure; exported for the CPU tests.
+extern "C" double steps_b200_order_incoherence(const void *x, int n, int real_bytes, double L) {
+    if (!x || n < 2 || !(L > 0.0) || (real_bytes != 8 && real_bytes != 4)) return 0.0;
+    const int samples = std::min(n - 1, 4096);
+    const size_t stride = (size_t)(n - 1) / samples;
+    std::vector<double> d((size_t)samples);
+    auto coord = [&](size_t i, int k) {
+        return real_bytes == 8 ? static_cast<const double *>(x)[3 * i + k] : (double)static_cast<const float *>(x)[3 * i + k];
+    };
+    for (int q = 0; q < samples; ++q) {
+        const size_t i = (size_t)q * stride;
+        double r2 = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            double dk = coord(i + 1, k) - coord(i, k);
+            if (fabs(dk) > 0.5 * L) dk -= copysign(L, dk);
+            r2 += dk * dk;
+        }
+        d[q] = sqrt(r2);
+    }
+    std::nth_element(d.begin(), d.begin() + samples / 2, d.end());
+    return d[samples / 2] / (L / cbrt((double)n));
 }
 
 extern "C" int steps_b200_group_permutation(steps_b200_group *g, int *perm_out) {

@@ -94,7 +94,7 @@ __host__ __device__ constexpr int sym_base_generic(int nwarps, int stages, int j
     return stages * tj * jrec_bytes + 2 * nwarps * 3 * tj * elem + 2 * stages * 8;
 }
 
-template <typename T, int TOPO, int R, int THREADS, int TJ, int STAGES, int MINB, bool FAST, bool PREFETCH = false>
+template <typename T, int TOPO, int R, int THREADS, int TJ, int STAGES, int MINB, bool FAST>
 __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const SymLaunchArgs sa, const TopoParams tp) {
     using JRec = typename JRecOf<T>::type;
     constexpr int NWARPS = THREADS / 32;
@@ -215,22 +215,6 @@ __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const 
 #pragma unroll 1
                 for (int s2 = 0; s2 < 32; ++s2) {
                     const int jidx = g0 + ((lane + s2) & 31);
-                    if (FAST && PREFETCH) {
-                        // ask L1 for the table rows of the NEXT visiting record's pairs while this step's are contracted
-                        const int jn1 = s2 < 31 ? g0 + ((lane + s2 + 1) & 31) : g0 + 32 + lane;
-                        if (jn1 < jn) {
-                            const JRec qn = Tl[jn1];
-#pragma unroll
-                            for (int r = 0; r < R; ++r) {
-                                T ex = (T)qn.x - xi[r], ey = (T)qn.y - yi[r], ez = (T)qn.z - zi[r];
-                                const T Lh = (T)fk.halfL, Lf = (T)fk.L;
-                                if (fabs(ex) > Lh) ex -= copysign(Lf, ex);
-                                if (fabs(ey) > Lh) ey -= copysign(Lf, ey);
-                                if (fabs(ez) > Lh) ez -= copysign(Lf, ez);
-                                t3_prefetch_rows<T>(fk, ex, ey, ez);
-                            }
-                        }
-                    }
                     if (jidx < jn) {
                         const JRec q = Tl[jidx];
 #pragma unroll

@@ -97,12 +97,17 @@ __host__ __device__ __forceinline__ void s1r2_correction_rz(const T *__restrict_
     const AxisStencil<T> sr = rho_stencil<T>(order, rho, rho_max, nrho);
     const AxisStencil<T> sz = z_stencil<T>(order, z, Lz, nz);
     T d0 = 0, d1 = 0;
-    for (int q = 0; q < sz.n; ++q) {
-        for (int p = 0; p < sr.n; ++p) {
-            const T w = sr.w[p] * sz.w[q];
-            const T *__restrict__ e = tab + ((size_t)sr.idx[p] * (size_t)nz + (size_t)sz.idx[q]) * 2u;
-            d0 += w * table_ld(e);
-            d1 += w * table_ld(e + 1);
+    // (fully unrolled with guards: the stencils stay in registers; the tap counts are uniform over a launch)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            if (q < sz.n && p < sr.n) {
+                const T w = sr.w[p] * sz.w[q];
+                const T *__restrict__ e = tab + ((size_t)sr.idx[p] * (size_t)nz + (size_t)sz.idx[q]) * 2u;
+                d0 += w * table_ld(e);
+                d1 += w * table_ld(e + 1);
+            }
         }
     }
     Drho = d0;

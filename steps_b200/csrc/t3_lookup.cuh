@@ -211,42 +211,6 @@ __host__ __device__ __forceinline__ void t3_correction_zwin(const T3Lookup &k, T
     D[0] = s0; D[1] = s1; D[2] = s2;
 }
 
-// Software prefetch of the 16 stencil rows of one displacement into L1 (device only): addresses only, no weights, no registers
-// held.  The gather of the action-reaction kernel is latency bound -- eight warps per SM cannot cover an L2 round trip per batch of
-// rows -- so the kernel asks for the rows of the NEXT pair of a lane while it contracts the current one.
-template <typename T>
-__device__ __forceinline__ void t3_prefetch_rows(const T3Lookup &k, T dx, T dy, T dz) {
-#ifdef __CUDA_ARCH__
-    const T halfL = (T)k.halfL, inv_h = (T)k.inv_h;
-    const int N = k.N;
-    constexpr int NC = t3_copies<T>();
-    constexpr int LINE = 128 / (int)sizeof(T);  // reals per cache line
-    const int RS = t3_row_stride<T>(N);
-    auto first_of = [N](T u) {
-        int f = (int)floor(u) - 1;
-        if (f < 0) f += N;
-        if ((unsigned)f >= (unsigned)N) f = wrap_index(f, N);
-        return f;
-    };
-    int ix[4], iy[4];
-    axis_indices(first_of((dx + halfL) * inv_h - (T)0.5), N, ix);
-    axis_indices(first_of((dy + halfL) * inv_h - (T)0.5), N, iy);
-    const int z0 = first_of((dz + halfL) * inv_h - (T)0.5);
-    const int shift = (NC - (3 * z0) % NC) % NC;
-    const T *__restrict__ win = static_cast<const T *>(k.zwin) + (size_t)shift * t3_copy_elems<T>(N) + (size_t)(shift + 3 * z0);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const T *__restrict__ row = win + (size_t)(ix[a] * N + iy[b]) * (size_t)RS;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
-            // the 12 values straddle a line boundary when they start in its last 11 reals
-            if ((int)((reinterpret_cast<size_t>(row) / sizeof(T)) & (LINE - 1)) > LINE - 12) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 11));
-        }
-    }
-#endif
-}
-
 // aligned row copies of a row-major table: copy c holds row (x, y) at reals [c, c + 3 (N + 3)) of its row slot, z-entries N .. N+2
 // repeating 0 .. 2.  One call fills one (copy, row).
 template <typename T>

@@ -132,3 +132,66 @@ def test_group_in_spatial_order_gives_the_callers_order_back(case):
     assert np.allclose(ea, eb, rtol=1e-10)
     assert np.abs(xa - xb).max() / scale < 1e-12
     assert np.abs(Fa - Fb).max() / np.abs(Fa).max() < 1e-11
+
+
+def test_order_incoherence_separates_lattice_order_from_shuffled_input():
+    """the measure behind the automatic decision of group_upload() for T^3: ~1 in lattice order, ~N^(1/3)/2 when shuffled, ~1 again
+    once sorted by table cell (host-only, pure)"""
+    lib = _lib.load()
+    c = ic.t3_lattice(24, 61, L=100.0, is_periodic=2)
+    n = c.g.N
+    inc = lib.steps_b200_order_incoherence(c.x.ctypes.data, n, 8, 100.0)
+    assert 0.5 < inc < 2.0
+    rng = np.random.default_rng(3)
+    xs = np.ascontiguousarray(c.x.reshape(-1, 3)[rng.permutation(n)].reshape(-1))
+    inc_s = lib.steps_b200_order_incoherence(xs.ctypes.data, n, 8, 100.0)
+    assert inc_s > 6.0
+    perm = order(xs, 63)
+    xo = np.ascontiguousarray(xs.reshape(-1, 3)[perm].reshape(-1))
+    assert lib.steps_b200_order_incoherence(xo.ctypes.data, n, 8, 100.0) < 4.0
+    x32 = xs.astype(np.float32)
+    assert abs(lib.steps_b200_order_incoherence(x32.ctypes.data, n, 4, 100.0) - inc_s) < 1e-3 * inc_s
+    assert lib.steps_b200_order_incoherence(None, n, 8, 100.0) == 0.0
+
+
+@pytest.mark.gpu
+def test_t3_group_sorts_an_incoherent_input_by_itself():
+    """no set_spatial_order call: a shuffled T^3 input is kept sorted by table cell on the device (group_permutation exists), a
+    lattice-ordered one is left alone; either way the caller gets its own order back and the same forces to rounding"""
+    from oracle import pyref
+
+    if not pyref.available("t3_f64"):
+        pytest.skip("T^3 table needs oracle/_ref")
+    c = ic.t3_lattice(12, 61, L=30.0, is_periodic=2)
+    r = pyref.Reference("t3_f64")
+    r.configure(c.g, 400)
+    r.build_tables()
+    r.export_tables(c.g)
+    g = c.g
+    lib = _lib.load()
+
+    def run(x, M, S):
+        g.M, g.SOFT_LENGTH = M, S
+        grp = C.c_void_p()
+        p = g.cparams()
+        _lib.check(lib.steps_b200_group_create(C.byref(grp), C.byref(p), 8, 1, 0))
+        _lib.check(lib.steps_b200_group_upload(grp, x.ctypes.data, None, M.ctypes.data, S.ctypes.data, None))
+        _lib.check(lib.steps_b200_group_forces(grp))
+        perm = np.empty(g.N, dtype=np.int32)
+        has_perm = lib.steps_b200_group_permutation(grp, perm.ctypes.data_as(PI)) == 0
+        F = np.empty(3 * g.N)
+        xb = np.empty(3 * g.N)
+        _lib.check(lib.steps_b200_group_download(grp, xb.ctypes.data, None, F.ctypes.data))
+        lib.steps_b200_group_destroy(grp)
+        assert np.array_equal(xb, x)
+        return has_perm, F
+
+    M0, S0 = g.M.copy(), g.SOFT_LENGTH.copy()
+    sorted_a, Fa = run(c.x, M0, S0)
+    assert not sorted_a
+    sh = np.random.default_rng(5).permutation(g.N)
+    xs = np.ascontiguousarray(c.x.reshape(-1, 3)[sh].reshape(-1))
+    sorted_b, Fb = run(xs, np.ascontiguousarray(M0[sh]), np.ascontiguousarray(S0[sh]))
+    assert sorted_b
+    ref = Fa.reshape(-1, 3)[sh]
+    assert np.abs(Fb.reshape(-1, 3) - ref).max() / np.abs(ref).max() < 1e-12

@@ -293,12 +293,16 @@ def make_roofline(args, c, eng, world, pk_ms, ms_step, pairs_per_launch, peak_su
         sms = 148
         clock_hz = eng_clock_hz(peak_burst, rb)
         peak_gbs = 128.0 * sms * clock_hz / 1e9
-        achieved = 64 * 3 * rb * pairs_per_launch / (pk_ms * 1e-3) / 1e9
+        evaluations = pairs_per_launch / 2.0 if symmetric else pairs_per_launch  # gathers actually performed
+        achieved = 64 * 3 * rb * evaluations / (pk_ms * 1e-3) / 1e9
         return dict(common, bound="l1", achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
-                    table_bytes_per_directed_pair=64 * 3 * rb,
-                    peak_source="128 B/clk/SM x 148 SMs x the SM clock implied by the live FMA microbenchmark (L1 data-path width, "
-                                "tools/ubench_loads.cu); the action-reaction kernel reads the table once per unordered pair, so frac > 0.5 "
-                                "already means less than one full gather per directed pair",
+                    table_bytes_per_evaluation=64 * 3 * rb, evaluations_per_launch=evaluations,
+                    frac_counting_directed_pairs=64 * 3 * rb * pairs_per_launch / (pk_ms * 1e-3) / 1e9 / peak_gbs,
+                    peak_measured_gbs=120.0 * sms * clock_hz / 1e9,
+                    peak_source="L1 data path: 128 B/clk/SM x 148 SMs x the SM clock implied by the live FMA microbenchmark; tools/ubench_loads.cu "
+                                "measured 120 B/clk/SM for 128-bit loads on this GPU type (profiles/r2c_ubench_loads.txt), peak_measured_gbs.  "
+                                "achieved counts the 64 x 24 B of table one EVALUATION consumes; the action-reaction kernel evaluates each unordered "
+                                "pair once, so per directed pair of the reference it needs half of that (frac_counting_directed_pairs)",
                     fp64_tflops_at_20flop=FLOP_PER_PAIR * pairs_per_launch / (pk_ms * 1e-3) / 1e12)
     ev = evals_per_pair(g)
     achieved_tf = FLOP_PER_PAIR * ev * pairs_per_launch / (pk_ms * 1e-3) / 1e12
@@ -388,7 +392,7 @@ def parity_block(c, eng, world, rank, dist, dev, fn_pack):
             "note": "forces held by the engines after the last timed step (rows gathered from the owning ranks) vs the reference's CPU forces() on the same positions"}
 
 
-def reference_cuda_leg(c, target_s=6.0):
+def reference_cuda_leg(c, target_s=8.0):
     """the kernel to beat: the reference's OWN CUDA path (forces_cuda.cu compiled unmodified for sm_100a by
     `make -C oracle refcuda`) timed on this GPU on a bounded row range of the same workload, through its own host-buffer call."""
     import numpy as np
@@ -407,7 +411,7 @@ def reference_cuda_leg(c, target_s=6.0):
     lo = g.N // 4
     r.forces(c.x, lo, min(lo + 255, g.N - 1), 0)  # context, first allocation
     # size the timed call for about target_s seconds (its fixed cost -- allocation, H2D of x, M, SOFT_LENGTH -- is part of the call)
-    probe = min(4096, g.N - lo)
+    probe = min(16384, g.N - lo)
     t0 = time.perf_counter()
     r.forces(c.x, lo, lo + probe - 1, 0)
     tp = time.perf_counter() - t0
@@ -416,8 +420,12 @@ def reference_cuda_leg(c, target_s=6.0):
     r.forces(c.x, lo, lo + rows - 1, 0)
     t = time.perf_counter() - t0
     return {"value": rows * float(g.N) / t, "unit": UNIT, "rows": int(rows), "seconds": t, "e2e": True,
+            "threads_with_work": min(1.0, rows / (32.0 * 148 * 256)),
             "what": "the reference's forces() built with -DUSE_CUDA (ForceKernel*, forces_cuda.cu) for sm_100a, unmodified; its call copies "
-                    "x, M, SOFT_LENGTH in and F out every time, so this is an end-to-end figure; compare with our e2e"}
+                    "x, M, SOFT_LENGTH in and F out every time, so this is an end-to-end figure; compare with our e2e.  The reference kernel is "
+                    "parallel over i only (one i-particle per thread of a <<<32 x SMs, 256>>> grid, forces_cuda.cu:522-563): a bounded row sample "
+                    "leaves the fraction 1 - threads_with_work of its threads idle, so its whole-range throughput is higher than this sample's "
+                    "(profiles/r2a_reference_cuda_bench.txt: 1.8e10 pairs/s at C2 with 65536 rows)"}
 
 
 # ------------------------------------------------------------------------------------------------ our arm

@@ -377,19 +377,52 @@ def parity_block(c, eng, world, rank, dist, dev, fn_pack):
         return None
     x_now = eng.download(want_v=False, want_F=False)[0]
     kind, fn, cores = fn_pack
+    single = g.REAL.__name__ != "float64"
     t0 = time.perf_counter()
     ref = np.concatenate([np.asarray(fn(lo, hi, x_now), dtype=np.float64).reshape(-1, 3) for lo, hi in blocks])
     S = np.concatenate([pyport.force_norms(g, x_now, lo, hi, cores) for lo, hi in blocks])
+    out = {"rows": int(nrows), "blocks": [[int(lo), int(hi)] for lo, hi in blocks], "checker": kind}
+    tol = 1e-5 if single else 1e-12
+    if single and g.topology == 0:
+        # Single precision: two FP32 sums over N terms differ by the summation noise of BOTH (the reference adds its 1.7e7 terms one
+        # after the other in FP32).  The yardstick is therefore the double-precision reference on the same (promoted) inputs; the
+        # reference's own single-precision result is measured against it beside ours.
+        truth = fp64_truth(c, x_now, blocks, cores)
+        d_ours = np.linalg.norm(mine - truth, axis=1) / np.maximum(S, 1e-300)
+        d_ref = np.linalg.norm(ref - truth, axis=1) / np.maximum(S, 1e-300)
+        out.update({"yardstick": "the reference built in double precision (oracle/_ref r3_f64) on the promoted single-precision inputs",
+                    "max_dF_over_sum_abs_fij": float(d_ours.max()),
+                    "reference_single_precision_build_vs_yardstick": float(d_ref.max()),
+                    "ours_vs_reference_single_precision_build": float((np.linalg.norm(mine - ref, axis=1) / np.maximum(S, 1e-300)).max())})
+        ref = truth
+    else:
+        out["max_dF_over_sum_abs_fij"] = float((np.linalg.norm(mine - ref, axis=1) / np.maximum(S, 1e-300)).max())
     t_cpu = time.perf_counter() - t0
-    dF = np.linalg.norm(mine - ref, axis=1)
-    rel_noise = dF / np.maximum(S, 1e-300)
-    rel_F = dF / np.maximum(np.linalg.norm(ref, axis=1), 1e-300)
-    tol = 1e-12 if g.REAL.__name__ == "float64" else 1e-5
-    ok = bool(rel_noise.max() <= tol)
-    return {"rows": int(nrows), "blocks": [[int(lo), int(hi)] for lo, hi in blocks], "checker": kind, "tolerance": tol,
-            "max_dF_over_sum_abs_fij": float(rel_noise.max()), "p99_dF_over_F": float(np.percentile(rel_F, 99)), "max_dF_over_F": float(rel_F.max()),
-            "passed": ok, "cpu_seconds": round(t_cpu, 2),
-            "note": "forces held by the engines after the last timed step (rows gathered from the owning ranks) vs the reference's CPU forces() on the same positions"}
+    rel_F = np.linalg.norm(mine - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-300)
+    out.update({"tolerance": tol, "p99_dF_over_F": float(np.percentile(rel_F, 99)), "max_dF_over_F": float(rel_F.max()),
+                "passed": bool(out["max_dF_over_sum_abs_fij"] <= tol), "cpu_seconds": round(t_cpu, 2),
+                "note": "forces held by the engines after the last timed step (rows gathered from the owning ranks) vs the reference's CPU forces() on the same positions"})
+    return out
+
+
+def fp64_truth(c, x_now, blocks, cores):
+    """sampled rows from the reference compiled in double precision, fed the single-precision inputs promoted to double"""
+    import copy
+
+    import numpy as np
+
+    from oracle import pyport, pyref
+
+    g64 = copy.copy(c.g)
+    g64.REAL = np.float64
+    g64.M = np.ascontiguousarray(c.g.M, dtype=np.float64)
+    g64.SOFT_LENGTH = np.ascontiguousarray(c.g.SOFT_LENGTH, dtype=np.float64)
+    x64 = np.ascontiguousarray(x_now, dtype=np.float64)
+    if pyref.available("r3_f64"):
+        r = pyref.Reference("r3_f64")
+        r.configure(g64)
+        return np.concatenate([np.asarray(r.forces(x64, lo, hi, cores), dtype=np.float64).reshape(-1, 3) for lo, hi in blocks])
+    return np.concatenate([pyport.forces(g64, x64, lo, hi, cores).reshape(-1, 3) for lo, hi in blocks])
 
 
 def reference_cuda_leg(c, target_s=8.0):

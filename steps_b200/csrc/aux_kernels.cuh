@@ -176,18 +176,16 @@ __device__ __forceinline__ T cylindrical_force_correction(T r, T R, const T *__r
 template <typename T>
 __global__ void reduce_kernel(const T *__restrict__ fpart, int n_chunks, int fstride, int n_i, int id_min,
                               const T *__restrict__ x, T *__restrict__ F, const TopoParams tp, const T *__restrict__ fsym,
-                              size_t fsym_stride, const int2 *__restrict__ crange = nullptr, int ib_size = 1) {
+                              size_t fsym_stride, const unsigned long long *__restrict__ cmask = nullptr, int mask_words = 0,
+                              int ib_size = 1) {
     const int il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il >= n_i) return;
     T fx = 0, fy = 0, fz = 0;
-    // action-reaction launch: only the chunks [lo, hi) that intersect the i-block's tiles hold a partial sum for it
-    int c_lo = 0, c_hi = n_chunks;
-    if (crange) {
-        const int2 cr = crange[il / ib_size];
-        c_lo = cr.x;
-        c_hi = cr.y;
-    }
-    for (int c = c_lo; c < c_hi; ++c) {
+    // action-reaction launch: only the chunks in which one of the i-block's tile ranges has tiles hold a partial sum for it (one bit
+    // per chunk, built by the host from the rules; a block's ranges can leave whole chunks out in between)
+    const unsigned long long *__restrict__ mk = cmask ? cmask + (size_t)(il / ib_size) * mask_words : nullptr;
+    for (int c = 0; c < n_chunks; ++c) {
+        if (mk && !((mk[c >> 6] >> (c & 63)) & 1ull)) continue;
         const T *__restrict__ p = fpart + (size_t)c * 3 * fstride;
         fx += p[il];
         fy += p[fstride + il];

@@ -247,7 +247,8 @@ struct steps_b200_engine {
     int sched_sb = 0, sched_rows = 0, sched_chunks = 0, sched_tpc = 0;  // what the tables below were built for
     int2 *d_order = nullptr;             // per pass: its CTAs as (superblock within the pass, j-chunk), heaviest first
     std::vector<int> pass_cta_off;       // [n_passes + 1] offsets into d_order
-    int2 *d_crange = nullptr;            // per local i-block: the j-chunks [lo, hi) that hold a partial sum for it
+    unsigned long long *d_cmask = nullptr;  // per local i-block: one bit per j-chunk that holds a partial sum for it
+    int cmask_words = 0;
     // GLASS_MAKING mode: G = -1 and the diagnostics of step.cc:143-148, :270-303
     bool glass = false;
     double *d_glass_part = nullptr;  // [blocks][2*GLASS_NQ] per-block (sum, max) pairs
@@ -594,6 +595,7 @@ int build_sym_rules(int n, int nranks, int rank, int ib_size, int tj, std::vecto
 int setup_partition(steps_b200_engine *e, bool want_sym) {
     e->sym = false;
     e->h_rules.clear();
+    e->sched_sb = 0;  // the launch schedule was built from the old rules (sym_schedule)
     steps_b200_partition(e->n, e->nranks, e->rank, &e->i_lo, &e->i_hi);
     if (!want_sym || !(e->p.topology == STEPS_TOPO_R3 || tuned_s1r2(e) || gen_sym_topology(e))) return 0;
     const SymVariant sv = sym_shape(e);
@@ -650,6 +652,13 @@ extern "C" int steps_b200_sym_chunk_target(int n_tiles, int n_ib, long long rows
 }
 
 namespace {
+// debugging aid (STEPS_B200_POISON=1): scratch buffers are filled with NaN patterns when allocated, so that a partial sum that is read
+// without having been written shows up as a non-finite force instead of hiding behind the zeros of fresh device memory
+bool poison_scratch() {
+    static const bool on = getenv("STEPS_B200_POISON") != nullptr;
+    return on;
+}
+
 Plan sym_plan(const steps_b200_engine *e, int n_i) {
     const SymVariant sv = sym_shape(e);
     Plan p{};
@@ -827,7 +836,7 @@ template <typename T>
 int finish_pair_sym_t(steps_b200_engine *e, int id_min, int n_i, const Plan &pl) {
     reduce_kernel<T><<<(n_i + 255) / 256, 256, 0, e->stream>>>(static_cast<const T *>(e->d_fpart), pl.n_chunks, n_i, n_i, id_min,
                                                                 static_cast<const T *>(e->d_x), static_cast<T *>(e->d_F), e->tp,
-                                                                static_cast<const T *>(e->d_fsym), (size_t)e->n_pad, e->d_crange, pl.ib_size);
+                                                                static_cast<const T *>(e->d_fsym), (size_t)e->n_pad, e->d_cmask, e->cmask_words, pl.ib_size);
     e->launches++;
     CU_TRY(cudaGetLastError());
     return 0;
@@ -851,12 +860,19 @@ int sym_schedule(steps_b200_engine *e, const Plan &pl, int rows) {
         for (int k = 0; k < r.n_sym; ++k) n += std::max(0, std::min(r.sym_hi[k], c1) - std::max(r.sym_lo[k], c0));
         return n;
     };
-    std::vector<int2> crange(n_ib);
-    for (int ib = 0; ib < n_ib; ++ib) {
+    // chunk activity per i-block: the kernel treats (block, chunk) as work iff one of the block's tile ranges has a tile in the chunk
+    // (sym_hull of the rule restricted to the chunk) -- exactly those combinations get a partial sum written
+    const int words = (pl.n_chunks + 63) / 64;
+    std::vector<unsigned long long> cmask((size_t)n_ib * words, 0ull);
+    auto active = [&](int ib, int jc) {
+        const int c0 = jc * pl.tiles_per_chunk, c1 = std::min(c0 + pl.tiles_per_chunk, pl.n_tiles);
         int ha, hb;
-        sym_hull(e->h_rules[ib], 0, pl.n_tiles, ha, hb);
-        crange[ib] = ha < hb ? make_int2(ha / pl.tiles_per_chunk, (hb - 1) / pl.tiles_per_chunk + 1) : make_int2(0, 0);
-    }
+        sym_hull(e->h_rules[ib], c0, c1, ha, hb);
+        return ha < hb;
+    };
+    for (int ib = 0; ib < n_ib; ++ib)
+        for (int jc = 0; jc < pl.n_chunks; ++jc)
+            if (active(ib, jc)) cmask[(size_t)ib * words + (jc >> 6)] |= 1ull << (jc & 63);
     struct Cta { int gs, jc, cost; };
     std::vector<int2> order;
     std::vector<int> off(1, 0);
@@ -866,17 +882,13 @@ int sym_schedule(steps_b200_engine *e, const Plan &pl, int rows) {
         pass.clear();
         for (int gs = 0; gs < ns; ++gs) {
             const int ib_lo = (s0 + gs) * pl.sb, ib_hi = std::min(ib_lo + pl.sb, n_ib);
-            int c_lo = pl.n_chunks, c_hi = 0;
-            for (int ib = ib_lo; ib < ib_hi; ++ib)
-                if (crange[ib].x < crange[ib].y) { c_lo = std::min(c_lo, crange[ib].x); c_hi = std::max(c_hi, crange[ib].y); }
-            for (int jc = c_lo; jc < c_hi; ++jc) {
+            for (int jc = 0; jc < pl.n_chunks; ++jc) {
                 const int c0 = jc * pl.tiles_per_chunk, c1 = std::min(c0 + pl.tiles_per_chunk, pl.n_tiles);
                 int cost = 0, hull = 0;
                 for (int ib = ib_lo; ib < ib_hi; ++ib) {
+                    if (!((cmask[(size_t)ib * words + (jc >> 6)] >> (jc & 63)) & 1ull)) continue;
                     cost += tiles_in(e->h_rules[ib], c0, c1);
-                    int ha, hb;
-                    sym_hull(e->h_rules[ib], c0, c1, ha, hb);
-                    hull += std::max(0, hb - ha);
+                    hull += 1;
                 }
                 if (hull > 0) pass.push_back({gs, jc, cost});
             }
@@ -890,13 +902,14 @@ int sym_schedule(steps_b200_engine *e, const Plan &pl, int rows) {
         off.push_back((int)order.size());
     }
     if (e->d_order) CU_TRY(cudaFree(e->d_order));
-    if (e->d_crange) CU_TRY(cudaFree(e->d_crange));
+    if (e->d_cmask) CU_TRY(cudaFree(e->d_cmask));
     e->d_order = nullptr;
-    e->d_crange = nullptr;
+    e->d_cmask = nullptr;
     CU_TRY(cudaMalloc(&e->d_order, std::max<size_t>(1, order.size()) * sizeof(int2)));
-    CU_TRY(cudaMalloc(&e->d_crange, std::max<size_t>(1, crange.size()) * sizeof(int2)));
+    CU_TRY(cudaMalloc(&e->d_cmask, std::max<size_t>(1, cmask.size()) * sizeof(unsigned long long)));
     CU_TRY(cudaMemcpyAsync(e->d_order, order.data(), order.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
-    CU_TRY(cudaMemcpyAsync(e->d_crange, crange.data(), crange.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->d_cmask, cmask.data(), cmask.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
+    e->cmask_words = words;
     CU_TRY(cudaStreamSynchronize(e->stream));  // the vectors die here
     e->pass_cta_off.swap(off);
     e->sched_sb = pl.sb;
@@ -935,6 +948,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         }
         if (err != cudaSuccess) return fail(std::string("CUDA error: ") + cudaGetErrorString(err) + " allocating the j-side row buffer");
         e->gpart_bytes = rows * row_bytes;
+        if (poison_scratch()) CU_TRY(cudaMemset(e->d_gpart, 0xFF, e->gpart_bytes));
     }
     const int rows = (int)(e->gpart_bytes / row_bytes);
     const Plan pl = sym_plan(e, n_i);
@@ -948,6 +962,7 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
         e->fpart_bytes = 0;
         CU_TRY(cudaMalloc(&e->d_fpart, need));
         e->fpart_bytes = need;
+        if (poison_scratch()) CU_TRY(cudaMemset(e->d_fpart, 0xFF, need));
     }
     CU_TRY(cudaMemsetAsync(e->d_fsym, 0, row_bytes, e->stream));
     SymLaunchArgs sa{};
@@ -1225,7 +1240,7 @@ extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym, e->d_glass_part, e->d_glass, e->d_order, e->d_crange, e->d_table_zwin};
+    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym, e->d_glass_part, e->d_glass, e->d_order, e->d_cmask, e->d_table_zwin};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (e->h_errmax) cudaFreeHost(e->h_errmax);

@@ -58,6 +58,30 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
         : "memory");
 }
 
+// L2 residency hint for data a CTA writes and reads back a few milliseconds later (the i-side partial sums of the action-reaction
+// kernels between two windows): evict_last keeps those lines in L2 in preference to the streamed j-tiles and row segments.
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double ld_keep(const double *a, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_keep(const float *a, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_keep(double *a, double v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep(float *a, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
+}
+
 // ~2^-22 relative seed for 1/sqrt(x): one MUFU.RSQ64H on the high word (SFU pipe, not the FP64 pipe)
 __device__ __forceinline__ double rsqrt_seed(double x) {
     double y;

@@ -360,7 +360,8 @@ def parity_block(c, eng, world, rank, dist, dev, fn_pack):
 
     g = c.g
     N = g.N
-    blocks = sample_blocks(N)
+    # 512 rows (8 blocks of 64); half of that above 8M particles, where the CPU checker needs minutes per 512 rows and every GPU of the job waits
+    blocks = sample_blocks(N, 8, 64 if N <= 8_000_000 else 32)
     nrows = sum(hi - lo + 1 for lo, hi in blocks)
     mine = np.zeros((nrows, 3), dtype=np.float64)
     o = 0

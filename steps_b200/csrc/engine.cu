@@ -667,21 +667,23 @@ Plan sym_plan(const steps_b200_engine *e, int n_i) {
     p.n_tiles = e->n_tiles;
     p.slots = e->num_sms * sv.minb;
     // A CTA works through one superblock (sb i-blocks, one j-side row per superblock and tile: pair_r3_sym.cuh) x one j-chunk.  About half
-    // of the (superblock, chunk) combinations carry work (each unordered block pair is evaluated once), and the grid should hold >= 16
-    // waves of working CTAs: sb = 8 whenever the job is large enough for that, fewer for small jobs; then as many chunks as it takes.
-    const long long needed = 32LL * p.slots;
-    const int max_chunks = std::max(1, p.n_tiles / MIN_TILES_PER_CHUNK);
+    // of the (superblock, chunk) combinations carry work (each unordered block pair is evaluated once) and most of those cost the same
+    // (sb x tiles_per_chunk units), so a launch loses about half a CTA duration to its last, partly filled wave: 3.6 % at 31 waves
+    // (C2 on 8 GPUs with the first rule of round 2, profiles/r2m8_bench_c2.json).  Aim at >= 128 waves of working CTAs per pass:
+    // as many chunks as that takes, down to one window of tiles per chunk and within 32 GB of i-side partial sums; 8 blocks per
+    // superblock only where the job is large enough to still get there.
+    const long long needed = 256LL * p.slots;
+    const size_t row_bytes = (size_t)3 * e->n_pad * e->real_bytes;
+    const size_t rows = e->gpart_bytes ? e->gpart_bytes / row_bytes : std::max<size_t>(1, ((size_t)16 << 30) / row_bytes);
+    const int min_tpc = p.n_tiles >= 4096 ? 16 : MIN_TILES_PER_CHUNK;
+    const long long fp_cap = std::max<long long>(SYM_TARGET_CHUNKS, ((long long)32 << 30) / std::max<long long>(1, (long long)3 * n_i * e->real_bytes));
+    const int max_chunks = (int)std::max<long long>(1, std::min<long long>(p.n_tiles / min_tpc, fp_cap));
     p.sb = (int)std::max<long long>(1, std::min<long long>(SYM_SB_MAX, (long long)p.n_ib * max_chunks / needed));
     if (const char *s = getenv("STEPS_B200_SYM_SB")) p.sb = std::max(1, std::min(SYM_SB_LIMIT, atoi(s)));
     p.n_sb = (p.n_ib + p.sb - 1) / p.sb;
-    int target = (int)std::max<long long>(SYM_TARGET_CHUNKS, std::min<long long>(256, (needed + p.n_sb - 1) / p.n_sb));
-    if (const char *s = getenv("STEPS_B200_SYM_CHUNKS")) {
-        target = std::max(1, atoi(s));  // tuning knob
-    } else {
-        const size_t row_bytes = (size_t)3 * e->n_pad * e->real_bytes;
-        const size_t rows = e->gpart_bytes ? e->gpart_bytes / row_bytes : std::max<size_t>(1, ((size_t)16 << 30) / row_bytes);
-        target = std::max(target, steps_b200_sym_chunk_target(p.n_tiles, p.n_sb, (long long)rows, p.slots));
-    }
+    const long long per_pass = std::max<long long>(1, std::min<long long>(p.n_sb, (long long)rows));
+    int target = (int)std::min<long long>(max_chunks, std::max<long long>(SYM_TARGET_CHUNKS, (needed + per_pass - 1) / per_pass));
+    if (const char *s = getenv("STEPS_B200_SYM_CHUNKS")) target = std::max(1, atoi(s));  // tuning knob
     p.tiles_per_chunk = std::max(MIN_TILES_PER_CHUNK, (p.n_tiles + target - 1) / target);
     p.n_chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
     p.ctas = p.n_sb * p.n_chunks;
@@ -932,10 +934,10 @@ int launch_pair_sym(steps_b200_engine *e, int id_min, int n_i, Plan &plan_out) {
     if (!e->d_gpart) {
         size_t free_b = 0, total_b = 0;
         CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = std::min((size_t)16 << 30, free_b / 3);
+        size_t budget = std::min((size_t)64 << 30, free_b * 2 / 5);  // one row per superblock and pass: C5 on 8 GPUs fits one pass in 51 GB
         if (const char *s = getenv("STEPS_B200_SYM_GPART_MB")) budget = (size_t)atoll(s) << 20;
         size_t rows = std::max<size_t>(1, budget / row_bytes);
-        rows = std::min<size_t>(rows, (size_t)n_ib_call);  // (one row per superblock is what a pass needs: never more than this)
+        rows = std::min<size_t>(rows, (size_t)sym_plan(e, n_i).n_sb);  // one row per superblock is all a single pass needs
         // a smaller buffer only means more passes: halve until the allocation succeeds
         cudaError_t err = cudaErrorMemoryAllocation;
         while (rows >= 1) {

@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const 
     __syncthreads();
     int nsym = 0;
     int K0 = 0;  // tiles streamed so far by this CTA (pipeline stage / parity bookkeeping, pair_r3_sym.cuh)
+    const uint64_t keep = l2_policy_keep();  // the i-side sums come back within milliseconds: ask L2 to hold them (ptx_helpers.cuh)
     static_assert(!FAST || TOPO == 1, "lean arithmetic exists for T^3 only");
     const T3Lookup fk = t3_lookup_of<T>(tp);
     // (the engine launches the FAST instantiation only for IS_PERIODIC >= 2: the nearest-image-only sum has no table)
@@ -176,9 +177,9 @@ __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const 
         if (first || il0 >= a.n_i) {
             ax[r] = ay[r] = az[r] = 0;
         } else {  // sums of the earlier windows of this chunk
-            ax[r] = fp[il0];
-            ay[r] = fp[a.fstride + il0];
-            az[r] = fp[2 * (size_t)a.fstride + il0];
+            ax[r] = ld_keep(fp + il0, keep);
+            ay[r] = ld_keep(fp + a.fstride + il0, keep);
+            az[r] = ld_keep(fp + 2 * (size_t)a.fstride + il0, keep);
         }
     }
 
@@ -267,9 +268,9 @@ __global__ void __launch_bounds__(THREADS, MINB) force_generic_sym_kernel(const 
     for (int r = 0; r < R; ++r) {
         const int il = ib * IB + r * THREADS + tid;
         if (il < a.n_i) {
-            fp[il] = ax[r];
-            fp[a.fstride + il] = ay[r];
-            fp[2 * (size_t)a.fstride + il] = az[r];
+            st_keep(fp + il, ax[r], keep);
+            st_keep(fp + a.fstride + il, ay[r], keep);
+            st_keep(fp + 2 * (size_t)a.fstride + il, az[r], keep);
         }
     }
     }  // i-blocks of the superblock

@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const S
     const WarpBounds32 *__restrict__ wb = wb_s + warp;
     int nsym = 0;
     int K0 = 0;  // tiles streamed so far by this CTA (pipeline stage / parity bookkeeping, pair_r3_sym.cuh)
+    const uint64_t keep = l2_policy_keep();  // the i-side sums come back within milliseconds: ask L2 to hold them (ptx_helpers.cuh)
 
     for (int w0 = TA; w0 < TB; w0 += WB) {
     const int w1 = min(w0 + WB, TB);
@@ -187,9 +188,9 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const S
             if (first || il0 >= a.n_i) {
                 ax[r] = ay[r] = az[r] = 0.f;
             } else {  // sums of the earlier windows of this chunk
-                ax[r] = fp[il0];
-                ay[r] = fp[a.fstride + il0];
-                az[r] = fp[2 * (size_t)a.fstride + il0];
+                ax[r] = ld_keep(fp + il0, keep);
+                ay[r] = ld_keep(fp + a.fstride + il0, keep);
+                az[r] = ld_keep(fp + 2 * (size_t)a.fstride + il0, keep);
             }
             lo[0] = fminf(lo[0], me.x); hi[0] = fmaxf(hi[0], me.x);
             lo[1] = fminf(lo[1], me.y); hi[1] = fmaxf(hi[1], me.y);
@@ -324,9 +325,9 @@ __global__ void __launch_bounds__(THREADS, MINB) force_r3_f32_sym_kernel(const S
     for (int r = 0; r < R; ++r) {
         const int il = ib * IB + r * THREADS + tid;
         if (il < a.n_i) {
-            fp[il] = ax[r];
-            fp[a.fstride + il] = ay[r];
-            fp[2 * (size_t)a.fstride + il] = az[r];
+            st_keep(fp + il, ax[r], keep);
+            st_keep(fp + a.fstride + il, ay[r], keep);
+            st_keep(fp + 2 * (size_t)a.fstride + il, az[r], keep);
         }
     }
     }  // i-blocks of the superblock

@@ -277,6 +277,10 @@ typedef struct steps_b200_cosmo {
 double steps_b200_friedmann_step(const steps_b200_cosmo *c, double a0, double h);
 double steps_b200_hubble(const steps_b200_cosmo *c, double a);
 double steps_b200_next_timestep(double acc_param, double errmax, double h_min, double h_max);
+/* the same with the output-time clamp of main.cc:1843-1846: with outputs scheduled in time (OUTPUT_TIME_VARIABLE == 0) a step that would pass
+ * t_next ends 1e-9 h_min after it */
+double steps_b200_next_timestep_to_output(double acc_param, double errmax, double h_min, double h_max, double T, double t_next,
+                                          int output_time_variable);
 
 /* FP64 / FP32 FMA-pipe microbenchmark on `device`: returns measured TFLOP/s (2 flop per FMA) --
  * the roofline denominator for this path. */

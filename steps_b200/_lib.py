@@ -123,6 +123,7 @@ SYMBOLS = {
     "steps_b200_friedmann_step": (_D, [C.POINTER(CCosmo), _D, _D]),
     "steps_b200_hubble": (_D, [C.POINTER(CCosmo), _D]),
     "steps_b200_next_timestep": (_D, [_D, _D, _D, _D]),
+    "steps_b200_next_timestep_to_output": (_D, [_D, _D, _D, _D, _D, _D, _I]),
     "steps_b200_fma_peak": (_I, [_I, _I, _PD, _PD]),
     "steps_b200_fma_peak_sustained": (_I, [_I, _I, _D, _PD]),
 }

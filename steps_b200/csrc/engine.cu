@@ -2350,6 +2350,16 @@ extern "C" double steps_b200_next_timestep(double acc_param, double errmax, doub
     return h;
 }
 
+// main.cc:1834-1846 in full, for callers that keep the output schedule themselves (a standalone Engine user; the step() shim runs inside
+// main.cc, which applies the clamp itself): when outputs are scheduled in time (OUTPUT_TIME_VARIABLE == 0) a step never overshoots the
+// next output time t_next -- it ends 1e-9 h_min past it.
+extern "C" double steps_b200_next_timestep_to_output(double acc_param, double errmax, double h_min, double h_max, double T, double t_next,
+                                                     int output_time_variable) {
+    double h = steps_b200_next_timestep(acc_param, errmax, h_min, h_max);
+    if (h + T > t_next && output_time_variable == 0) h = t_next - T + 1e-9 * h_min;
+    return h;
+}
+
 extern "C" int steps_b200_fma_peak(int device, int real_bytes, double *tflops_out, double *sm_clock_mhz_out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

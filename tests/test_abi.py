@@ -107,6 +107,11 @@ def test_host_scalars_match_golden():
     assert lib.steps_b200_next_timestep(0.005, 1e8, 1e-7, 1e-3) == pytest.approx(math.sqrt(2 * 0.005 / 1e8))
     assert lib.steps_b200_next_timestep(0.005, 1e20, 1e-7, 1e-3) == 1e-7
     assert lib.steps_b200_next_timestep(0.005, 1e-9, 1e-7, 1e-3) == 1e-3
+    # main.cc:1843-1846: outputs scheduled in time -> the step ends 1e-9 h_min past the next output time; scheduled in redshift -> untouched
+    f = lib.steps_b200_next_timestep_to_output
+    assert f(0.005, 1e-9, 1e-7, 1e-3, 0.9995, 1.0, 0) == pytest.approx(1.0 - 0.9995 + 1e-16, rel=1e-12)
+    assert f(0.005, 1e-9, 1e-7, 1e-3, 0.9995, 1.0, 1) == 1e-3
+    assert f(0.005, 1e-9, 1e-7, 1e-3, 0.5, 1.0, 0) == 1e-3
 
 
 def test_ic_shapes():

@@ -30,8 +30,19 @@ def engine_forces(c, symmetric):
     return F, used, shape
 
 
+_TRUTH = {}
+
+
 def truth64(c):
-    """FP64 forces and force scales of the FP32 inputs (same rounded masses, softening lengths, positions)"""
+    """FP64 forces and force scales of the FP32 inputs (same rounded masses, softening lengths, positions); cached per input (the
+    CPU sum takes a minute at N = 40 000 and several tests share an input)"""
+    key = (c.g.N, float(np.asarray(c.x, dtype=np.float64).sum()))
+    if key not in _TRUTH:
+        _TRUTH[key] = _truth64(c)
+    return _TRUTH[key]
+
+
+def _truth64(c):
     g = c.g
     g64 = copy.copy(g)
     g64.REAL = np.float64

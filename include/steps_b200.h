@@ -149,6 +149,15 @@ int steps_b200_engine_set_symmetric(steps_b200_engine *e, int on);
 int steps_b200_engine_is_symmetric(steps_b200_engine *e);
 int steps_b200_engine_range(steps_b200_engine *e, int *i_lo, int *i_hi);
 int steps_b200_sym_rules(int n, int nranks, int rank, int ib_size, int *i_lo, int *i_hi, int *rules_out, int max_blocks);
+/* Host-only (no GPU needed): rules -> launch plan -> schedule of rank `rank` of `nranks` for an n-particle job of the given topology
+ * (STEPS_TOPO_*) and precision; row_budget_bytes = memory for the j-side rows (0: 16 GB).  plan_out[8] = {ib_size, n_ib, sb, n_sb,
+ * n_chunks, tiles_per_chunk, n_tiles, n_passes}; order_out = (superblock within its pass, chunk) int pairs of all passes one after
+ * the other, pass_off_out[n_passes + 1] their offsets; cmask_out = one bit per (local i-block, chunk) that gets a partial sum written,
+ * *words_out 64-bit words per block.  Returns the number of CTAs of the evaluation, -1 when the action-reaction path does not apply,
+ * -2 when an output array is too small. */
+int steps_b200_sym_schedule_host(int n, int nranks, int rank, int topology, int real_bytes, long long row_budget_bytes, int *plan_out,
+                                 int *order_out, int max_ctas, int *pass_off_out, int max_passes, unsigned long long *cmask_out,
+                                 long long max_mask_words, int *words_out);
 /* Host-only, pure: the number of j-chunks the action-reaction launch aims for, given the j-tiles of the problem, the i-blocks of the
  * call, the j-side rows one pass holds and the resident-CTA slots of the GPU (see engine.cu; 56 unless a pass would have < 24 waves). */
 int steps_b200_sym_chunk_target(int n_tiles, int n_ib, long long rows_per_pass, int slots);

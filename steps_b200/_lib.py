@@ -79,6 +79,7 @@ SYMBOLS = {
     "steps_b200_engine_is_symmetric": (_I, [_VP]),
     "steps_b200_engine_range": (_I, [_VP, _PI, _PI]),
     "steps_b200_sym_rules": (_I, [_I, _I, _I, _I, _PI, _PI, _PI, _I]),
+    "steps_b200_sym_schedule_host": (_I, [_I, _I, _I, _I, _I, C.c_longlong, _PI, _PI, _I, _PI, _I, C.POINTER(C.c_ulonglong), C.c_longlong, _PI]),
     "steps_b200_sym_chunk_target": (_I, [_I, _I, C.c_longlong, _I]),
     "steps_b200_engine_debug_set_rank": (_I, [_VP, _I, _I, _I]),
     "steps_b200_engine_debug_fsym": (_I, [_VP, _VP, _VP, _PI]),

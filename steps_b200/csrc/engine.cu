@@ -508,11 +508,12 @@ bool gen_sym_env_default() {
     return v == 1 && sym_env_default();
 }
 bool gen_sym_topology(const steps_b200_engine *e) { return e->p.topology == STEPS_TOPO_T3 || e->p.topology == STEPS_TOPO_S1R2_LOOKUP; }
-SymVariant sym_shape(const steps_b200_engine *e) {
-    if (gen_sym_topology(e)) return GEN_SYM_VARIANTS[gen_sym_variant()];
-    if (e->p.topology == STEPS_TOPO_S1R2_NOLOOKUP) return S1R2_SYM_VARIANTS[s1r2_sym_variant()];
-    return e->real_bytes == 8 ? SYM_VARIANTS[sym_variant()] : SYM32_VARIANTS[sym32_variant()];
+SymVariant sym_shape_of(int topology, int real_bytes) {
+    if (topology == STEPS_TOPO_T3 || topology == STEPS_TOPO_S1R2_LOOKUP) return GEN_SYM_VARIANTS[gen_sym_variant()];
+    if (topology == STEPS_TOPO_S1R2_NOLOOKUP) return S1R2_SYM_VARIANTS[s1r2_sym_variant()];
+    return real_bytes == 8 ? SYM_VARIANTS[sym_variant()] : SYM32_VARIANTS[sym32_variant()];
 }
+SymVariant sym_shape(const steps_b200_engine *e) { return sym_shape_of(e->p.topology, e->real_bytes); }
 // whether an engine takes the action-reaction path when the caller has not said so
 bool sym_default_for(const steps_b200_engine *e) {
     if (e->p.topology == STEPS_TOPO_R3) return e->real_bytes == 8 ? sym_env_default() : sym_f32_env_default();
@@ -659,8 +660,15 @@ bool poison_scratch() {
     return on;
 }
 
+// the launch plan of an action-reaction evaluation of n_i rows: a pure function of the sizes (host-only; steps_b200_sym_schedule_host
+// runs it without a device for the CPU tests)
+Plan sym_plan_of(const SymVariant sv, int n_i, int n_tiles, int n_pad, int real_bytes, int num_sms, size_t gpart_bytes);
 Plan sym_plan(const steps_b200_engine *e, int n_i) {
-    const SymVariant sv = sym_shape(e);
+    return sym_plan_of(sym_shape(e), n_i, e->n_tiles, e->n_pad, e->real_bytes, e->num_sms, e->gpart_bytes);
+}
+Plan sym_plan_of(const SymVariant sv, int n_i, int n_tiles_, int n_pad, int real_bytes, int num_sms, size_t gpart_bytes) {
+    struct { int n_tiles, n_pad, real_bytes, num_sms; size_t gpart_bytes; } E{n_tiles_, n_pad, real_bytes, num_sms, gpart_bytes};
+    const auto *e = &E;
     Plan p{};
     p.ib_size = sv.R * sv.threads;
     p.n_ib = (n_i + p.ib_size - 1) / p.ib_size;
@@ -853,10 +861,9 @@ int finish_pair_sym(steps_b200_engine *e, int id_min, int n_i, const Plan &pl) {
 // Host schedule of the action-reaction launch for plan pl with `rows` superblock rows per pass: for every pass the list of its CTAs
 // (superblock within the pass, j-chunk) that have work at all, heaviest first (cost = tiles the CTA evaluates, from the rules), ties in
 // chunk-major order so that concurrently running CTAs share their j-tiles in L2; and per i-block the chunks that will hold a partial sum.
-int sym_schedule(steps_b200_engine *e, const Plan &pl, int rows) {
-    if (e->d_order && e->sched_sb == pl.sb && e->sched_rows == rows && e->sched_chunks == pl.n_chunks && e->sched_tpc == pl.tiles_per_chunk)
-        return 0;
-    const int n_ib = (int)e->h_rules.size();
+void sym_schedule_build(const std::vector<SymRule> &rules, const Plan &pl, int rows, std::vector<int2> &order, std::vector<int> &off,
+                        std::vector<unsigned long long> &cmask, int &words) {
+    const int n_ib = (int)rules.size();
     auto tiles_in = [](const SymRule &r, int c0, int c1) {
         int n = std::max(0, std::min(r.diag_hi, c1) - std::max(r.diag_lo, c0));
         for (int k = 0; k < r.n_sym; ++k) n += std::max(0, std::min(r.sym_hi[k], c1) - std::max(r.sym_lo[k], c0));
@@ -864,20 +871,20 @@ int sym_schedule(steps_b200_engine *e, const Plan &pl, int rows) {
     };
     // chunk activity per i-block: the kernel treats (block, chunk) as work iff one of the block's tile ranges has a tile in the chunk
     // (sym_hull of the rule restricted to the chunk) -- exactly those combinations get a partial sum written
-    const int words = (pl.n_chunks + 63) / 64;
-    std::vector<unsigned long long> cmask((size_t)n_ib * words, 0ull);
+    words = (pl.n_chunks + 63) / 64;
+    cmask.assign((size_t)n_ib * words, 0ull);
     auto active = [&](int ib, int jc) {
         const int c0 = jc * pl.tiles_per_chunk, c1 = std::min(c0 + pl.tiles_per_chunk, pl.n_tiles);
         int ha, hb;
-        sym_hull(e->h_rules[ib], c0, c1, ha, hb);
+        sym_hull(rules[ib], c0, c1, ha, hb);
         return ha < hb;
     };
     for (int ib = 0; ib < n_ib; ++ib)
         for (int jc = 0; jc < pl.n_chunks; ++jc)
             if (active(ib, jc)) cmask[(size_t)ib * words + (jc >> 6)] |= 1ull << (jc & 63);
     struct Cta { int gs, jc, cost; };
-    std::vector<int2> order;
-    std::vector<int> off(1, 0);
+    order.clear();
+    off.assign(1, 0);
     std::vector<Cta> pass;
     for (int s0 = 0; s0 < pl.n_sb; s0 += rows) {
         const int ns = std::min(rows, pl.n_sb - s0);
@@ -889,7 +896,7 @@ int sym_schedule(steps_b200_engine *e, const Plan &pl, int rows) {
                 int cost = 0, hull = 0;
                 for (int ib = ib_lo; ib < ib_hi; ++ib) {
                     if (!((cmask[(size_t)ib * words + (jc >> 6)] >> (jc & 63)) & 1ull)) continue;
-                    cost += tiles_in(e->h_rules[ib], c0, c1);
+                    cost += tiles_in(rules[ib], c0, c1);
                     hull += 1;
                 }
                 if (hull > 0) pass.push_back({gs, jc, cost});
@@ -903,6 +910,16 @@ int sym_schedule(steps_b200_engine *e, const Plan &pl, int rows) {
         for (const Cta &c : pass) order.push_back(make_int2(c.gs, c.jc));
         off.push_back((int)order.size());
     }
+}
+
+int sym_schedule(steps_b200_engine *e, const Plan &pl, int rows) {
+    if (e->d_order && e->sched_sb == pl.sb && e->sched_rows == rows && e->sched_chunks == pl.n_chunks && e->sched_tpc == pl.tiles_per_chunk)
+        return 0;
+    std::vector<int2> order;
+    std::vector<int> off;
+    std::vector<unsigned long long> cmask;
+    int words = 0;
+    sym_schedule_build(e->h_rules, pl, rows, order, off, cmask, words);
     if (e->d_order) CU_TRY(cudaFree(e->d_order));
     if (e->d_cmask) CU_TRY(cudaFree(e->d_cmask));
     e->d_order = nullptr;
@@ -1280,6 +1297,44 @@ extern "C" int steps_b200_sym_rules(int n, int nranks, int rank, int ib_size, in
     static_assert(sizeof(SymRule) == 16 * sizeof(int), "rule = 16 ints");
     if (rules_out) memcpy(rules_out, rules.data(), rules.size() * sizeof(SymRule));
     return (int)rules.size();
+}
+
+// Host-only (no device needed): rules -> launch plan -> schedule of rank `rank` of `nranks` for an N-particle job of the given
+// topology / precision, with `row_budget_bytes` for the j-side rows (0: the library's default of 16 GB for this purpose).  plan_out[8] =
+// {ib_size, n_ib, sb, n_sb, n_chunks, tiles_per_chunk, n_tiles, n_passes}; order_out = (superblock within pass, chunk) pairs of all passes
+// one after the other, pass_off_out[n_passes + 1] their offsets; cmask_out = one bit per (local i-block, chunk) that gets a partial sum,
+// `words_out` 64-bit words per block.  Returns the number of CTAs, -1 when the action-reaction path does not apply, -2 when an output
+// array is too small.  tests/test_sym_rules.py checks that the kernel's own activity rule, the mask and the CTA list agree.
+extern "C" int steps_b200_sym_schedule_host(int n, int nranks, int rank, int topology, int real_bytes, long long row_budget_bytes, int *plan_out,
+                                            int *order_out, int max_ctas, int *pass_off_out, int max_passes, unsigned long long *cmask_out,
+                                            long long max_mask_words, int *words_out) {
+    if (n <= 0 || nranks < 1 || rank < 0 || rank >= nranks || (real_bytes != 8 && real_bytes != 4)) return -1;
+    const SymVariant sv = sym_shape_of(topology, real_bytes);
+    std::vector<SymRule> rules;
+    int lo = 0, hi = 0;
+    if (build_sym_rules(n, nranks, rank, sv.R * sv.threads, TJ, rules, &lo, &hi)) return -1;
+    const int n_tiles = (n + TJ - 1) / TJ, n_pad = n_tiles * TJ;
+    const size_t row_bytes = (size_t)3 * n_pad * real_bytes;
+    const size_t budget = row_budget_bytes > 0 ? (size_t)row_budget_bytes : ((size_t)16 << 30);
+    Plan pl = sym_plan_of(sv, hi - lo, n_tiles, n_pad, real_bytes, 148, 0);
+    const size_t rows = std::max<size_t>(1, std::min<size_t>(budget / row_bytes, (size_t)pl.n_sb));
+    pl = sym_plan_of(sv, hi - lo, n_tiles, n_pad, real_bytes, 148, rows * row_bytes);
+    std::vector<int2> order;
+    std::vector<int> off;
+    std::vector<unsigned long long> cmask;
+    int words = 0;
+    sym_schedule_build(rules, pl, (int)rows, order, off, cmask, words);
+    const int n_passes = (int)off.size() - 1;
+    if ((int)order.size() > max_ctas || n_passes > max_passes || (long long)cmask.size() > max_mask_words) return -2;
+    if (plan_out) {
+        const int v[8] = {pl.ib_size, pl.n_ib, pl.sb, pl.n_sb, pl.n_chunks, pl.tiles_per_chunk, pl.n_tiles, n_passes};
+        memcpy(plan_out, v, sizeof(v));
+    }
+    if (order_out) memcpy(order_out, order.data(), order.size() * sizeof(int2));
+    if (pass_off_out) memcpy(pass_off_out, off.data(), off.size() * sizeof(int));
+    if (cmask_out) memcpy(cmask_out, cmask.data(), cmask.size() * sizeof(unsigned long long));
+    if (words_out) *words_out = words;
+    return (int)order.size();
 }
 
 // ---- test hooks of the multi-GPU action-reaction path on ONE device (tests/test_gpu_sym.py) ----

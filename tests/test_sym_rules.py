@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import steps_b200 as sb
-from steps_b200 import api
+from steps_b200 import _lib, api
 
 TJ = 128
 
@@ -100,3 +100,85 @@ def test_chunk_target_of_the_action_reaction_plan():
     # monotone in the rows a pass holds
     vals = [f(131072, 16384, r, sms * 4) for r in (40, 79, 160, 320, 640)]
     assert vals == sorted(vals, reverse=True) and vals[-1] == 56
+
+
+def _schedule(n, nranks, rank, topology=0, real_bytes=8, budget=0):
+    import ctypes as C
+
+    lib = _lib.load()
+    plan = (C.c_int * 8)()
+    max_ctas, max_passes, max_words = 4_000_000, 4096, 8_000_000
+    order = np.zeros(2 * max_ctas, dtype=np.int32)
+    off = np.zeros(max_passes + 1, dtype=np.int32)
+    mask = np.zeros(max_words, dtype=np.uint64)
+    words = C.c_int()
+    n_cta = lib.steps_b200_sym_schedule_host(n, nranks, rank, topology, real_bytes, budget, plan, order.ctypes.data_as(C.POINTER(C.c_int)), max_ctas,
+                                             off.ctypes.data_as(C.POINTER(C.c_int)), max_passes, mask.ctypes.data_as(C.POINTER(C.c_ulonglong)),
+                                             max_words, C.byref(words))
+    assert n_cta >= 0, n_cta
+    keys = ("ib_size", "n_ib", "sb", "n_sb", "n_chunks", "tpc", "n_tiles", "n_passes")
+    p = dict(zip(keys, plan))
+    return p, order[: 2 * n_cta].reshape(-1, 2), off[: p["n_passes"] + 1], mask[: p["n_ib"] * words.value].reshape(p["n_ib"], words.value)
+
+
+def _block_chunk_activity(rules, p):
+    """the kernel's own rule (pair_r3_sym.cuh sym_hull on the rule restricted to a chunk): a (block, chunk) is work -- and gets a
+    partial sum written -- iff one of the block's tile ranges has a tile inside the chunk"""
+    act = np.zeros((p["n_ib"], p["n_chunks"]), dtype=bool)
+    for b, r in enumerate(rules):
+        rngs = [(r[0], r[1])] + [(r[3 + k], r[8 + k]) for k in range(r[2])]
+        for lo, hi in rngs:
+            if lo < hi:
+                act[b, lo // p["tpc"]: (hi - 1) // p["tpc"] + 1] = True
+    return act
+
+
+@pytest.mark.parametrize("n,nranks,topology,real_bytes", [(6001, 2, 0, 8), (6001, 3, 0, 8), (40000, 2, 0, 4), (200000, 8, 0, 8), (2_000_000, 1, 0, 8),
+                                                         (2_000_000, 8, 0, 8), (262144, 4, 1, 8), (400000, 5, 3, 8), (16_777_216, 2, 0, 4)])
+def test_launch_schedule_covers_exactly_what_the_final_reduction_reads(n, nranks, topology, real_bytes):
+    """Host-only check of the action-reaction launch schedule (round 2): the chunk mask the final reduction reads, the kernel's own
+    activity rule and the list of launched CTAs must agree for every rank -- a block's tile ranges can leave whole chunks out in between
+    (ring assignment with gaps), which a contiguous chunk range got wrong and only a 2-GPU run with reused memory showed."""
+    for rank in sorted({0, nranks // 2, nranks - 1}):
+        p, order, off, mask = _schedule(n, nranks, rank, topology, real_bytes)
+        _, _, rules = api.sym_rules(n, nranks, rank, p["ib_size"])
+        rules = [[int(v) for v in r] for r in rules]
+        assert len(rules) == p["n_ib"] and p["n_sb"] == -(-p["n_ib"] // p["sb"]) and p["n_chunks"] == -(-p["n_tiles"] // p["tpc"])
+        act = _block_chunk_activity(rules, p)
+        bits = np.array([[(int(mask[b, c >> 6]) >> (c & 63)) & 1 for c in range(p["n_chunks"])] for b in range(p["n_ib"])], dtype=bool)
+        assert np.array_equal(bits, act), "chunk mask differs from the kernel's activity rule"
+        # superblock x chunk combinations that carry work, pass by pass: launched exactly once, nothing else launched
+        seen = set()
+        n_pad = p["n_tiles"] * TJ
+        rows = max(1, min((16 << 30) // (3 * n_pad * real_bytes), p["n_sb"]))  # superblock rows per pass, as the library sizes them
+        assert p["n_passes"] == -(-p["n_sb"] // rows)
+        for k in range(p["n_passes"]):
+            ctas = order[off[k]: off[k + 1]]
+            assert len(ctas) == 0 or int(ctas[:, 0].max()) < min(rows, p["n_sb"] - k * rows)
+            for gs, jc in ctas:
+                key = (k * rows + int(gs), int(jc))
+                assert key not in seen, "a (superblock, chunk) combination is launched twice"
+                seen.add(key)
+        want = set()
+        for S in range(p["n_sb"]):
+            blk = act[S * p["sb"]: (S + 1) * p["sb"]]
+            for jc in np.flatnonzero(blk.any(axis=0)):
+                want.add((S, int(jc)))
+        assert seen == want, "launched CTAs differ from the combinations that carry work"
+        # every tile of every symmetric or diagonal range lies in an active (block, chunk): nothing is skipped
+        for b, r in enumerate(rules):
+            for lo, hi in [(r[0], r[1])] + [(r[3 + k], r[8 + k]) for k in range(r[2])]:
+                for t in (lo, hi - 1):
+                    if lo < hi:
+                        assert act[b, t // p["tpc"]]
+
+
+def test_launch_schedule_multi_pass_and_wave_count():
+    """C5 on one GPU: the rows of all superblocks do not fit the buffer -> several passes, each with >= 100 waves' worth of working CTAs
+    unless the chunk count is at its cap; C2 on one GPU: one pass"""
+    p, order, off, _ = _schedule(16_777_216, 1, 0, 0, 4, 64 << 30)
+    assert p["n_passes"] > 1 and p["sb"] == 8
+    assert off[-1] == len(order)
+    p2, order2, off2, _ = _schedule(2_000_000, 1, 0, 0, 8, 64 << 30)
+    assert p2["n_passes"] == 1 and p2["sb"] == 8
+    assert len(order2) >= 100 * 296  # >= 100 waves of 2 CTAs x 148 SMs

@@ -142,7 +142,8 @@ _ORACLE = {}
 
 def _oracle_cached(c):
     """oracle forces and force scales of an input, computed once per test process (several tests share the N = 20 000 zoom input)"""
-    key = (c.g.N, float(c.x.sum()))
+    g = c.g
+    key = (g.N, np.asarray(c.x).tobytes(), np.asarray(g.M).tobytes(), np.asarray(g.SOFT_LENGTH).tobytes(), g.COSMOLOGY, g.COMOVING_INTEGRATION)
     if key not in _ORACLE:
         _ORACLE[key] = (pyport.forces(c.g, c.x, 0, c.g.N - 1), pyport.force_norms(c.g, c.x, 0, c.g.N - 1))
     return _ORACLE[key]

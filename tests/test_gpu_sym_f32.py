@@ -36,7 +36,8 @@ _TRUTH = {}
 def truth64(c):
     """FP64 forces and force scales of the FP32 inputs (same rounded masses, softening lengths, positions); cached per input (the
     CPU sum takes a minute at N = 40 000 and several tests share an input)"""
-    key = (c.g.N, float(np.asarray(c.x, dtype=np.float64).sum()))
+    g = c.g
+    key = (g.N, np.asarray(c.x).tobytes(), np.asarray(g.M).tobytes(), np.asarray(g.SOFT_LENGTH).tobytes(), g.COSMOLOGY, g.COMOVING_INTEGRATION)
     if key not in _TRUTH:
         _TRUTH[key] = _truth64(c)
     return _TRUTH[key]

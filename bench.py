@@ -271,13 +271,13 @@ def make_roofline(args, c, eng, world, pk_ms, ms_step, pairs_per_launch, peak_su
     N = g.N
     n_i = eng.i_hi - eng.i_lo
     topo = g.topology
-    traffic = None
+    traffic, traffic_source = None, None
     tr_path = os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")
     if os.path.exists(tr_path) and world == 1 and args.config == "c2" and not args.n:
         try:
             tr = json.load(open(tr_path))
-            traffic = {"dram_bytes_per_evaluation": tr.get("dram_bytes_per_launch"), "source": tr.get("source"),
-                       "note": "from an ncu --set full capture (not measured in this run): see the named profile"}
+            traffic = tr.get("dram_bytes_per_launch")  # dram__bytes_read.sum + dram__bytes_write.sum of one force evaluation (ncu)
+            traffic_source = ("NOT measured in this run: ncu capture of the same configuration committed under profiles/ -- " + str(tr.get("source")))
         except Exception:  # noqa: BLE001
             traffic = None
     # algorithmic DRAM bytes of one force evaluation on this rank: the j-stream once, the i-side inputs, F out
@@ -286,7 +286,7 @@ def make_roofline(args, c, eng, world, pk_ms, ms_step, pairs_per_launch, peak_su
     kname = {0: "force_r3_f64" if rb == 8 else "force_r3_f32", 1: "force_generic<T^3>", 2: "force_generic<S1xR2 lookup>",
              3: "force_s1r2nl_f64" if rb == 8 else "force_generic<S1xR2 NOLOOKUP>"}[topo] + ("_sym_kernel" if symmetric else "_kernel")
     common = {"kernel": kname, "pairs_per_launch": pairs_per_launch, "kernel_ms": pk_ms, "kernel_share_of_step": pk_ms / ms_step,
-              "traffic": traffic, "algorithmic_dram_bytes_per_launch": alg_bytes, "launch_shape": shape}
+              "traffic": traffic, "traffic_source": traffic_source, "algorithmic_dram_bytes_per_launch": alg_bytes, "launch_shape": shape}
     if topo == 1 and g.IS_PERIODIC >= 2:
         # L1 data path: 64 x 24 B of table per directed pair (what the reference's kernel reads per pair), delivered at
         # 128 B/clk/SM; peak = that rate at the SM clock the FMA microbenchmark implies for this GPU

@@ -273,6 +273,20 @@ int steps_b200_snapshot_ascii_host(const char *path, const void *x, const void *
                                    double h0_dimless, double a, int zero_velocities, int nthreads);
 int steps_b200_group_snapshot_ascii_async(steps_b200_group *g, const char *path, double h0_dimless, double a, int zero_velocities);
 int steps_b200_group_snapshot_wait(steps_b200_group *g);
+/* Redshift-cone output (write_redshift_cone, inputoutput.cc:314-405; called at main.cc:1785) with the state resident on the
+ * devices.  cone_select(): every resident particle with r_min <= |x| (all != 0: every particle) that no earlier call selected is flagged
+ * (the reference's IN_CONE) and its row is brought to the host; *count_out of them, kept in ascending order of the caller's particle index.
+ * cone_rows(): rows_out[count][8] REAL = x y z vx vy vz M pad, index_out[count]; either may be NULL.  cone_reset(): clear the flags.
+ * redshift_cone_ascii_host(): host-only formatter, appends to `path` exactly the lines the reference writes for these particles -- all == 0:
+ * "x y z vx vy vz M D z index" with out_list[z_index]; all != 0 (end of the run): the redshift of the radial bin the distance falls into
+ * (limits = r_bin_limits, descending) and D * H0_dimless.  cone_write_ascii(): the same for the rows of the last selection. */
+int steps_b200_group_cone_select(steps_b200_group *g, double r_min, int all, int *count_out);
+int steps_b200_group_cone_rows(steps_b200_group *g, void *rows_out, int *index_out);
+int steps_b200_group_cone_reset(steps_b200_group *g);
+int steps_b200_redshift_cone_ascii_host(const char *path, const void *rows, const int *index, int count, int real_bytes, double h0_dimless,
+                                        int all, const double *limits, int n_limits, const double *out_list, int z_index);
+int steps_b200_group_cone_write_ascii(steps_b200_group *g, const char *path, double h0_dimless, int all, const double *limits, int n_limits,
+                                      const double *out_list, int z_index);
 int steps_b200_group_download(steps_b200_group *g, void *x, void *v, void *F);
 
 /* ------------------------------------------------------------------------------------------

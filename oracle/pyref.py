@@ -156,6 +156,23 @@ class Reference:
         self.lib.sref_kdk_state(x.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p))
         return x, v, F
 
+    def write_redshift_cone(self, out_dir: str, x, v, limits, zlist, z_index: int, delta_z_index: int = 0, all_: int = 0,
+                            h0_independent_units: int = 0, reset: bool = False, t_next: float = 0.0) -> str:
+        """the reference's own write_redshift_cone (inputoutput.cc:314-405, ASCII branch): appends to <out_dir>redshift_cone.dat and keeps
+        its IN_CONE flags between calls unless reset; returns the path of the file"""
+        x = np.ascontiguousarray(x, dtype=self.REAL)
+        v = np.ascontiguousarray(v, dtype=self.REAL)
+        lim = np.ascontiguousarray(limits, dtype=np.float64)
+        zl = np.ascontiguousarray(zlist, dtype=np.float64)
+        if not out_dir.endswith("/"):
+            out_dir += "/"
+        self.lib.sref_write_redshift_cone.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                      C.c_int, C.c_int, C.c_int, C.c_double]
+        self.lib.sref_write_redshift_cone(out_dir.encode(), x.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), lim.ctypes.data_as(C.c_void_p),
+                                          lim.size, zl.ctypes.data_as(C.c_void_p), zl.size, z_index, delta_z_index, all_, h0_independent_units,
+                                          1 if reset else 0, t_next)
+        return out_dir + "redshift_cone.dat"
+
     def write_ascii_snapshot(self, out_dir: str, x, v, a: float, t_next: float, h0_independent_units: int = 0) -> str:
         """the reference's own write_ascii_snapshot (inputoutput.cc:826-909); returns the path of the file it wrote"""
         if not out_dir.endswith(os.sep):

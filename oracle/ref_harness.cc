@@ -52,6 +52,7 @@ void forces(REAL *x, REAL *F, int ID_min, int ID_max);                /* forces.
 extern double a_prev;
 
 void write_ascii_snapshot(REAL *x, REAL *v);  /* inputoutput.cc:826 (C++ linkage, declared in main.cc) */
+void write_redshift_cone(REAL *x, REAL *v, double *limits, int z_index, int delta_z_index, int ALL);  /* inputoutput.cc:314 */
 
 extern "C" {
 
@@ -318,6 +319,37 @@ int sref_write_ascii_snapshot(const char *dir, const REAL *x0, const REAL *v0, d
     OUTPUT_TIME_VARIABLE = 0;
     H0_INDEPENDENT_UNITS = h0_independent_units;
     write_ascii_snapshot(x, v);
+    return 0;
+}
+
+/* the reference's own redshift-cone writer (inputoutput.cc:314-405, ASCII branch) on the state given here: appends to
+ * <dir>redshift_cone.dat and updates IN_CONE; reset_flags != 0 starts from an empty cone.  limits[n_limits] = r_bin_limits (descending),
+ * zlist[n_limits - 1...] = out_list as main.cc holds them. */
+int sref_write_redshift_cone(const char *dir, const REAL *x0, const REAL *v0, const double *limits, int n_limits, const double *zlist, int n_z,
+                             int z_index, int delta_z_index, int all, int h0_independent_units, int reset_flags, double t_next_now)
+{
+    static double *own_limits = NULL, *own_z = NULL;
+    strncpy(OUT_DIR, dir, sizeof(OUT_DIR) - 1);
+    OUT_DIR[sizeof(OUT_DIR) - 1] = 0;
+    memcpy(x, x0, sizeof(REAL) * 3 * (size_t)N);
+    memcpy(v, v0, sizeof(REAL) * 3 * (size_t)N);
+    OUTPUT_FORMAT = 0;
+    H0_INDEPENDENT_UNITS = h0_independent_units;
+    t_next = t_next_now;
+    free(own_limits);
+    free(own_z);
+    own_limits = (double *)malloc(sizeof(double) * (size_t)n_limits);
+    own_z = (double *)malloc(sizeof(double) * (size_t)n_z);
+    memcpy(own_limits, limits, sizeof(double) * (size_t)n_limits);
+    memcpy(own_z, zlist, sizeof(double) * (size_t)n_z);
+    out_list = own_z;
+    out_list_size = n_z;
+    if (reset_flags || !IN_CONE) {
+        delete[] IN_CONE;
+        IN_CONE = new bool[N];
+        for (int i = 0; i < N; i++) IN_CONE[i] = false;
+    }
+    write_redshift_cone(x, v, own_limits, z_index, delta_z_index, all);
     return 0;
 }
 

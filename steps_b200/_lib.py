@@ -92,6 +92,11 @@ SYMBOLS = {
     "steps_b200_group_destroy": (None, [_VP]),
     "steps_b200_group_size": (_I, [_VP]),
     "steps_b200_group_engine": (_VP, [_VP, _I]),
+    "steps_b200_group_cone_select": (_I, [_VP, _D, _I, _PI]),
+    "steps_b200_group_cone_rows": (_I, [_VP, _VP, _PI]),
+    "steps_b200_group_cone_reset": (_I, [_VP]),
+    "steps_b200_redshift_cone_ascii_host": (_I, [C.c_char_p, _VP, _PI, _I, _I, _D, _I, _PD, _I, _PD, _I]),
+    "steps_b200_group_cone_write_ascii": (_I, [_VP, C.c_char_p, _D, _I, _PD, _I, _PD, _I]),
     "steps_b200_order_incoherence": (_D, [_VP, _I, _I, _D]),
     "steps_b200_group_upload": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "steps_b200_group_forces": (_I, [_VP]),

@@ -24,6 +24,7 @@
 #include "ewald_t3.cuh"
 #include "ewald_s1r2.cuh"
 #include "radial_table.cuh"
+#include "cone_select.cuh"
 
 using namespace steps;
 
@@ -228,6 +229,11 @@ struct steps_b200_engine {
     double *d_errmax = nullptr, *h_errmax = nullptr;
     size_t fpart_bytes = 0;
     size_t table_bytes = 0, radial_bytes = 0;
+    // redshift cone (cone_select.cuh): persistent flags + compaction buffers for this engine's own rows
+    unsigned char *d_in_cone = nullptr;
+    void *d_cone_rows = nullptr;
+    int *d_cone_idx = nullptr, *d_cone_count = nullptr;
+    int cone_cap = 0;
     void *d_table_zwin = nullptr;  // T^3: aligned row copies of the Ewald table (t3_lookup.cuh), rebuilt whenever the table is uploaded
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // force begin/end, step begin/end, pair kernel begin/end
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // caller-placed (bench)
@@ -1259,7 +1265,8 @@ extern "C" void steps_b200_engine_destroy(steps_b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym, e->d_glass_part, e->d_glass, e->d_order, e->d_cmask, e->d_table_zwin};
+    void *bufs[] = {e->d_x, e->d_v, e->d_F, e->d_m, e->d_s, e->d_smax, e->d_tinfo, e->d_jrec, e->d_fpart, e->d_table, e->d_radial, e->d_errmax, e->d_zflag, e->d_rules, e->d_gpart, e->d_fsym, e->d_glass_part, e->d_glass, e->d_order, e->d_cmask, e->d_table_zwin, e->d_in_cone, e->d_cone_rows, e->d_cone_idx,
+                    e->d_cone_count};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (e->h_errmax) cudaFreeHost(e->h_errmax);
@@ -1936,6 +1943,9 @@ struct steps_b200_group {
     bool order_explicit = false;  // the caller chose (set_spatial_order, also to switch it off): no automatic decision at upload
     std::vector<int> perm;
     std::vector<char> tmp[3];  // host staging for the permuted copies
+    // redshift cone: rows selected by the last group_cone_select, in ascending (caller's) particle index
+    std::vector<char> cone_rows;
+    std::vector<int> cone_index;
 };
 
 namespace {
@@ -2326,6 +2336,120 @@ static int group_download_raw(steps_b200_group *g, void *x, void *v, void *F) {
     for (auto *e : g->eng)
         if (steps_b200_engine_sync(e)) return 1;
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ redshift cone
+namespace {
+template <typename T>
+int engine_cone_select(steps_b200_engine *e, double r_min, int all, std::vector<char> &rows, std::vector<int> &index) {
+    DeviceGuard dg_;
+    CU_TRY(cudaSetDevice(e->device));
+    const int cnt = e->i_hi - e->i_lo;
+    if (!e->d_in_cone) {
+        CU_TRY(cudaMalloc(&e->d_in_cone, (size_t)e->n));
+        CU_TRY(cudaMemsetAsync(e->d_in_cone, 0, (size_t)e->n, e->stream));
+        CU_TRY(cudaMalloc(&e->d_cone_count, sizeof(int)));
+    }
+    if (e->cone_cap < cnt) {
+        if (e->d_cone_rows) CU_TRY(cudaFree(e->d_cone_rows));
+        if (e->d_cone_idx) CU_TRY(cudaFree(e->d_cone_idx));
+        e->d_cone_rows = nullptr;
+        e->d_cone_idx = nullptr;
+        CU_TRY(cudaMalloc(&e->d_cone_rows, (size_t)cnt * CONE_ROW * sizeof(T)));
+        CU_TRY(cudaMalloc(&e->d_cone_idx, (size_t)cnt * sizeof(int)));
+        e->cone_cap = cnt;
+    }
+    CU_TRY(cudaMemsetAsync(e->d_cone_count, 0, sizeof(int), e->stream));
+    if (cnt > 0) {
+        cone_select_kernel<T><<<(cnt + 255) / 256, 256, 0, e->stream>>>((const T *)e->d_x, (const T *)e->d_v, (const T *)e->d_m, e->d_in_cone, e->i_lo,
+                                                                        e->i_hi, r_min, all, (T *)e->d_cone_rows, e->d_cone_idx, e->d_cone_count);
+        e->launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    int count = 0;
+    CU_TRY(cudaMemcpyAsync(&count, e->d_cone_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    const size_t r0 = rows.size(), i0 = index.size();
+    rows.resize(r0 + (size_t)count * CONE_ROW * sizeof(T));
+    index.resize(i0 + (size_t)count);
+    if (count > 0) {
+        CU_TRY(cudaMemcpyAsync(rows.data() + r0, e->d_cone_rows, (size_t)count * CONE_ROW * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaMemcpyAsync(index.data() + i0, e->d_cone_idx, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return 0;
+}
+}  // namespace
+
+// Particles that enter the light cone now: every resident particle with r_min <= |x| (all != 0: every particle) that no earlier call
+// has selected.  Each engine scans its own rows on its device; only the selected rows come to the host, where they are put in
+// ascending order of the caller's particle index (the order in which the reference's loop meets them).
+extern "C" int steps_b200_group_cone_select(steps_b200_group *g, double r_min, int all, int *count_out) {
+    if (!g || !count_out) return fail("group or output is NULL");
+    std::vector<char> rows;
+    std::vector<int> index;
+    for (auto *e : g->eng) {
+        if (!e->have_state) return fail("engine has no particle state");
+        if (g->real_bytes == 8 ? engine_cone_select<double>(e, r_min, all, rows, index) : engine_cone_select<float>(e, r_min, all, rows, index)) return 1;
+    }
+    const size_t count = index.size(), rb = (size_t)CONE_ROW * g->real_bytes;
+    if (!g->perm.empty())
+        for (auto &i : index) i = g->perm[(size_t)i];  // resident order -> caller's order
+    std::vector<size_t> ord(count);
+    for (size_t k = 0; k < count; ++k) ord[k] = k;
+    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return index[a] < index[b]; });
+    g->cone_rows.resize(count * rb);
+    g->cone_index.resize(count);
+    for (size_t k = 0; k < count; ++k) {
+        memcpy(g->cone_rows.data() + k * rb, rows.data() + ord[k] * rb, rb);
+        g->cone_index[k] = index[ord[k]];
+    }
+    *count_out = (int)count;
+    return 0;
+}
+
+// the rows of the last selection: rows_out[count][8] REAL = x y z vx vy vz M (pad), index_out[count]; either may be NULL
+extern "C" int steps_b200_group_cone_rows(steps_b200_group *g, void *rows_out, int *index_out) {
+    if (!g) return fail("group is NULL");
+    if (rows_out && !g->cone_rows.empty()) memcpy(rows_out, g->cone_rows.data(), g->cone_rows.size());
+    if (index_out && !g->cone_index.empty()) memcpy(index_out, g->cone_index.data(), g->cone_index.size() * sizeof(int));
+    return 0;
+}
+
+// forget which particles are in the cone (a new run on the same group)
+extern "C" int steps_b200_group_cone_reset(steps_b200_group *g) {
+    if (!g) return fail("group is NULL");
+    for (auto *e : g->eng)
+        if (e->d_in_cone) {
+            DeviceGuard dg_;
+            CU_TRY(cudaSetDevice(e->device));
+            CU_TRY(cudaMemsetAsync(e->d_in_cone, 0, (size_t)e->n, e->stream));
+            CU_TRY(cudaStreamSynchronize(e->stream));
+        }
+    return 0;
+}
+
+// Appends the lines write_redshift_cone (inputoutput.cc:314-405, ASCII) writes for these particles (ascending index) to `path`.
+// Host-only.  limits = r_bin_limits (descending comoving distances), out_list = output redshifts, z_index = the bin reached.
+extern "C" int steps_b200_redshift_cone_ascii_host(const char *path, const void *rows, const int *index, int count, int real_bytes, double h0_dimless,
+                                                   int all, const double *limits, int n_limits, const double *out_list, int z_index) {
+    if (!path || (count > 0 && (!rows || !index)) || !limits || !out_list || z_index < 0 || z_index >= n_limits || (real_bytes != 8 && real_bytes != 4))
+        return fail("bad arguments");
+    const std::string text = real_bytes == 8 ? cone_format<double>((const double *)rows, index, count, h0_dimless, all, limits, n_limits, out_list, z_index)
+                                             : cone_format<float>((const float *)rows, index, count, h0_dimless, all, limits, n_limits, out_list, z_index);
+    FILE *f = fopen(path, "a");
+    if (!f) return fail(std::string("cannot open ") + path);
+    const bool ok = fwrite(text.data(), 1, text.size(), f) == text.size();
+    fclose(f);
+    return ok ? 0 : fail(std::string("short write to ") + path);
+}
+
+// the rows of the last group_cone_select straight into the file
+extern "C" int steps_b200_group_cone_write_ascii(steps_b200_group *g, const char *path, double h0_dimless, int all, const double *limits, int n_limits,
+                                                 const double *out_list, int z_index) {
+    if (!g) return fail("group is NULL");
+    return steps_b200_redshift_cone_ascii_host(path, g->cone_rows.data(), g->cone_index.data(), (int)g->cone_index.size(), g->real_bytes, h0_dimless, all,
+                                               limits, n_limits, out_list, z_index);
 }
 
 // ------------------------------------------------------------------------------------------------ host helpers

@@ -22,6 +22,13 @@ What the keys mean here (see DESIGN.md "Measurement"):
             peak = DFMA microbenchmark measured live on the same GPU (MEASURED_PEAKS.json has no FP64 entry).
   cpu_baseline  oracle/_ref (the unmodified reference, kind "reference") or the plain-C port (kind "port")
             on a bounded i-subrange of the same workload, all host threads.
+  parity    after the timed region: 512 sampled rows of the forces the engines hold (gathered from the owning ranks at N > 1)
+            against the reference's CPU forces() on the same positions; max |dF_i| / sum_j |f_ij| and `passed` (<= 1e-12 FP64;
+            single precision: <= 1e-5 against the reference built in double precision on the promoted inputs).
+  reference_cuda  the reference's own CUDA kernel (forces_cuda.cu built unmodified for sm_100a) timed on this GPU through its own
+            host-buffer call on a bounded row range (N = 1 only).
+  --config c1|c2|c3|c4|c5 selects the BASELINE.json configuration (default c2, the headline); the roofline of c3 (T^3) is the L1
+  data path, of the others the FP64 / FP32 pipe.
 PyTorch is used only for plumbing: torch.distributed rendezvous/barrier and pinned host buffers.
 """
 from __future__ import annotations
